@@ -1,0 +1,123 @@
+/*
+ * isp_tts_b200.h -- C ABI of the B200-native Aligner hot path of ilya16/isp-tts.
+ *
+ * The reference is pure Python; its "FFI" for this path is the pair of numba
+ * entry points that tts/models/acoustic/modules/alignment.py calls, plus the
+ * torch ops around them.  Each function below states the reference interface
+ * it replaces (paths relative to the reference root).  INTEGRATION.md shows the
+ * ctypes stubs a maintainer adds on the reference side.
+ *
+ * Conventions (all functions):
+ *   - plain pointers and sizes; no torch / numba types;
+ *   - every device buffer, workspace included, is allocated and owned by the
+ *     caller; the library never allocates, frees or synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream, which is what numba and torch use in the reference);
+ *   - pointers must belong to the current CUDA device, which must be sm_100;
+ *   - lengths are int64 and are read ON THE DEVICE (no host sync);
+ *     the contract is 1 <= len <= Tmax; out-of-range lengths are clamped for
+ *     memory safety and reported through isp_mas_status();
+ *   - return value: 0 = enqueued; < 0 = ISP_ERR_* (bad argument / unsupported
+ *     shape / workspace too small); > 0 = a cudaError_t.  isp_last_error()
+ *     returns a thread-local message for the last non-zero return;
+ *   - re-entrant; the only process-wide state is a per-device one-time
+ *     cudaFuncSetAttribute.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef ISP_TTS_B200_H
+#define ISP_TTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISP_OK               0
+#define ISP_ERR_INVALID     (-1)  /* null pointer, non-positive size, bad stride/alignment */
+#define ISP_ERR_UNSUPPORTED (-2)  /* shape outside what the kernels cover (see each function) */
+#define ISP_ERR_WORKSPACE   (-3)  /* ws_bytes < isp_*_workspace_bytes(...) */
+#define ISP_ERR_DEVICE      (-4)  /* current device is not compute capability 10.x */
+
+/* element types of the encoded operands of isp_loglik_forward */
+#define ISP_DTYPE_F32  0          /* fp32 in memory, TF32 tensor-core products, fp32 accumulate */
+#define ISP_DTYPE_BF16 1          /* bf16 in memory, fp32 accumulate */
+
+#define ISP_MAS_MAX_T2   2048     /* text tokens per utterance the MAS kernel covers */
+#define ISP_LOGLIK_MAX_T2 512     /* text tokens per utterance the fused GEMM covers (TMEM columns) */
+#define ISP_LOGLIK_MAX_D  256     /* attention_dim */
+
+int         isp_version(void);            /* 10000*major + 100*minor + patch */
+const char* isp_last_error(void);
+/* 0 if the current device can run the kernels (sm_100), else ISP_ERR_DEVICE / cudaError_t */
+int         isp_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Monotonic Alignment Search + hard path + durations.
+ *
+ * Replaces, in one launch:
+ *   cuda_b_mas[(max(64,B),1),(1,256)](log_p, prev_log_p, prev_ind, attn_out, in_lens, out_lens)
+ *       tts/modules/aligner/cuda_mas.py:11-46, launched at
+ *       tts/models/acoustic/modules/alignment.py:328-330 (with the clone / three
+ *       zeros_like at :321-326, which are not needed here), and its CPU twin
+ *   b_mas(b_attn_map, in_lens, out_lens)            tts/modules/aligner/mas.py:30-35
+ *   attn_hard.sum(dim=1)                            alignment.py:275
+ *
+ * logp      (B, T1max, T2max) fp32 log-likelihoods, element strides sB/sT1/sT2;
+ *           sT2 must be 1.  NOT modified (the reference's GPU route works on a clone).
+ *           Rows are frames (mel), columns are text tokens.
+ * text_len  (B) int64 = in_lens;  mel_len (B) int64 = out_lens.
+ * attn_hard (B, T1max, T2max) int16, contiguous, FULLY written: exactly one 1 per
+ *           valid frame, 0 elsewhere (padding included) -- it need not be pre-zeroed.
+ * durations (B, T2max) int64, contiguous, fully written; may be NULL.
+ * ws        isp_mas_workspace_bytes(B,T1max,T2max) bytes, 16 B aligned; holds the packed
+ *           backpointer bits when they do not fit in shared memory, and the status word.
+ * Limits:   T2max <= ISP_MAS_MAX_T2; T1max < 2^24.
+ * Results are bit-identical to the reference for NaN-free input.
+ */
+size_t isp_mas_workspace_bytes(int B, int T1max, int T2max);
+int    isp_mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
+                       const int64_t* text_len, const int64_t* mel_len,
+                       int B, int T1max, int T2max,
+                       int16_t* attn_hard, int64_t* durations,
+                       void* ws, size_t ws_bytes, void* stream);
+/* Reads back (synchronously, after the stream drains) how many utterances had a length
+ * outside [1, Tmax] in the last isp_mas_forward that used `ws`.  -1 on error. */
+int    isp_mas_status(const void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pairwise log-likelihood: batched Q.K^T GEMM with the whole epilogue fused.
+ *
+ * Replaces ConvAttention.forward from the matmul on
+ *   tts/models/acoustic/modules/alignment.py:189-208 :
+ *   torch.matmul (:189), scale (:190), clamp (:192), batch_diagonal_prior (:18-37, :195),
+ *   log_softmax over ALL T2max columns + log(prior + 1e-6) (:196), clone (:198),
+ *   masked_fill + softmax (:201-203), mask multiply (:206).
+ *
+ * Q  (B, T1max, D)  = queries_enc.transpose(1,2) of :187, row-major, D contiguous
+ * K  (B, T2max, D)  = keys_enc.transpose(1,2)    of :182, row-major, D contiguous
+ *    dtype ISP_DTYPE_F32 or ISP_DTYPE_BF16; base 16 B aligned; D % 8 == 0, D <= ISP_LOGLIK_MAX_D.
+ * scale             = attention_dim ** -0.5 (:116)
+ * attn_logits, attn_soft  (B, T1max, T2max) fp32 contiguous, fully written (:208).
+ * attention_prior   non-zero = the reference default (:194); 0 = plain scaled scores.
+ * Limits: T2max <= ISP_LOGLIK_MAX_T2.
+ * Accuracy: within 1e-3 relative of the fp32 reference (tests state the tolerance).
+ */
+size_t isp_loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
+int    isp_loglik_forward(const void* Q, const void* K, int dtype,
+                          const int64_t* text_len, const int64_t* mel_len,
+                          int B, int T1max, int T2max, int D, float scale, int attention_prior,
+                          float* attn_logits, float* attn_soft,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* Tuning knobs for benchmarks/tests (process-wide, not part of the drop-in contract).
+ *   "mas.cols_per_lane"  4 | 8 | 0 (= heuristic)
+ *   "mas.ring_rows"      rows of logits kept in flight per utterance, 0 = heuristic
+ * Returns the previous value, or ISP_ERR_INVALID for an unknown key. */
+int isp_set_option(const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISP_TTS_B200_H */

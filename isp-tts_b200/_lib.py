@@ -1,0 +1,86 @@
+"""ctypes binding of libisp_tts_b200.so (the C ABI in include/isp_tts_b200.h).
+
+No fallback: if the library is missing or the device is not a B200-class GPU,
+every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_PKG, "libisp_tts_b200.so")
+
+ISP_DTYPE_F32 = 0
+ISP_DTYPE_BF16 = 1
+
+EXPORTS = [
+    "isp_version", "isp_last_error", "isp_device_check",
+    "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_status",
+    "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_set_option",
+]
+
+_lib = None
+
+
+class IspError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise IspError(
+            f"{SO_PATH} is missing: build it with `python -m isp_tts_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU or PyTorch fallback for this path.")
+    lib = ctypes.CDLL(SO_PATH)
+    c_int, c_i64, c_sz, vp, f32 = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_float
+    lib.isp_version.restype = c_int
+    lib.isp_last_error.restype = ctypes.c_char_p
+    lib.isp_device_check.restype = c_int
+    lib.isp_mas_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.isp_mas_workspace_bytes.restype = c_sz
+    lib.isp_mas_forward.argtypes = [vp, c_i64, c_i64, c_i64, vp, vp, c_int, c_int, c_int, vp, vp, vp, c_sz, vp]
+    lib.isp_mas_forward.restype = c_int
+    lib.isp_mas_status.argtypes = [vp, vp]
+    lib.isp_mas_status.restype = c_int
+    lib.isp_loglik_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.isp_loglik_workspace_bytes.restype = c_sz
+    lib.isp_loglik_forward.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, f32, c_int, vp, vp, vp, c_sz, vp]
+    lib.isp_loglik_forward.restype = c_int
+    lib.isp_set_option.argtypes = [ctypes.c_char_p, c_int]
+    lib.isp_set_option.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().isp_last_error().decode("utf-8", "replace")
+        raise IspError(f"{what} failed (code {rc}): {msg}")
+
+
+def set_option(key: str, value: int) -> int:
+    rc = load().isp_set_option(key.encode(), int(value))
+    if rc == -1 and key not in ("mas.cols_per_lane", "mas.ring_rows", "loglik.debug_scores"):
+        raise IspError(f"unknown option {key!r}")
+    return rc
+
+
+_checked_devices = set()
+
+
+def require_device(device) -> None:
+    """Raise unless `device` is a CUDA device the kernels were built for."""
+    import torch
+    if device.type != "cuda":
+        raise IspError(f"tensor is on {device}; this path runs on a B200 (CUDA, sm_100) only -- there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _checked_devices:
+        return
+    with torch.cuda.device(idx):
+        check(load().isp_device_check(), "isp_device_check")
+    _checked_devices.add(idx)

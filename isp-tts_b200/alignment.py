@@ -1,0 +1,386 @@
+"""Aligner / ConvAttention with the reference's constructor, forward signature,
+outputs and state_dict keys; the hot path runs in the sm_100a kernels.
+
+Mirrors tts/models/acoustic/modules/alignment.py of the reference:
+  batch_diagonal_prior :18-37   ConvBlock1D :40-83   ConvAttention :98-208
+  AlignerOutput :216-220        Aligner :223-331
+What is different underneath:
+  * from the matmul on (:189-208) everything is ONE fused kernel (isp_loglik_forward):
+    tcgen05 GEMM + scale + log_softmax + closed-form diagonal prior + masked softmax;
+  * MAS, the dense hard path and the durations (:272-275, :291-331) are ONE kernel
+    (isp_mas_forward); there is no numba, no CPU route, no device->host check per step;
+  * the last 1x1 projection of each stack is evaluated as a matmul that emits the
+    (B, T, D) layout the GEMM's TMA loads want (same weights, same state_dict keys).
+The conv stacks themselves are still torch ops ("next").
+"""
+from __future__ import annotations
+
+import inspect
+import warnings
+from collections.abc import Sequence
+from dataclasses import dataclass
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+from torch.nn import functional as F
+
+from . import _lib
+from .mas import mas_forward
+
+__all__ = ["batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
+           "Aligner", "AlignerConfig", "AlignerOutput", "loglik_forward"]
+
+MISSING = "???"   # same sentinel string omegaconf uses; the reference's configs compare against it
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers the reference takes from tts/utils/functions.py and tts/modules/{layers,normalization}.py
+# ----------------------------------------------------------------------------------------------
+def _length_mask(lengths: Tensor, max_len: int) -> Tensor:
+    """(B, max_len) bool, True on valid positions.  No .item() sync (functions.py:61-66 has one)."""
+    return torch.arange(max_len, device=lengths.device)[None, :] < lengths[:, None]
+
+
+_ACTIVATIONS = {
+    "linear": nn.Identity, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU, "selu": nn.SELU, "tanh": nn.Tanh,
+    "mish": nn.Mish, "swish": nn.SiLU, "gelu": nn.GELU, "sigmoid": nn.Sigmoid,
+}   # tts/modules/layers.py:9-31
+
+
+def _masked_normalize(x: Tensor, mask: Tensor, dims, eps: float):
+    cnt = mask.sum(dims, keepdim=True)
+    mean = (x * mask).sum(dims, keepdim=True) / cnt
+    var = (((x * mask - mean) * mask) ** 2).sum(dims, keepdim=True) / cnt
+    return mean, var
+
+
+class MaskedInstanceNorm1d(nn.InstanceNorm1d):
+    """Instance norm whose statistics only see valid positions (normalization.py:104-124, 160-208)."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1,
+                 affine: bool = True, track_running_stats: bool = False):
+        super().__init__(num_features, eps, momentum, affine, track_running_stats)
+
+    def forward(self, x: Tensor, mask: Tensor | None = None) -> Tensor:
+        if mask is None:
+            return super().forward(x)
+        mean, var = _masked_normalize(x, mask.to(x.dtype), [2], self.eps)
+        y = (x - mean) / (var + self.eps).sqrt()
+        if self.weight is not None and self.bias is not None:
+            y = y * self.weight.view(1, -1, 1) + self.bias.view(1, -1, 1)
+        return y
+
+
+class MaskedBatchNorm1d(nn.BatchNorm1d):
+    """Batch norm over valid positions only (normalization.py:15-66, 160-208)."""
+
+    def forward(self, x: Tensor, mask: Tensor | None = None) -> Tensor:
+        if mask is None:
+            return super().forward(x)
+        use_batch_stats = self.training or (self.running_mean is None and self.running_var is None)
+        if use_batch_stats:
+            mean, var = _masked_normalize(x, mask.to(x.dtype), [0, 2], self.eps)
+            if self.training and self.track_running_stats:
+                mom = 0.0 if self.momentum is None else self.momentum
+                if self.num_batches_tracked is not None:
+                    self.num_batches_tracked.add_(1)
+                    if self.momentum is None:
+                        mom = 1.0 / float(self.num_batches_tracked)
+                with torch.no_grad():
+                    self.running_mean.mul_(1 - mom).add_(mom * mean.detach().view(-1))
+                    self.running_var.mul_(1 - mom).add_(mom * var.detach().view(-1))
+        else:
+            mean, var = self.running_mean.view(1, -1, 1), self.running_var.view(1, -1, 1)
+        y = (x - mean) / (var + self.eps).sqrt()
+        if self.weight is not None and self.bias is not None:
+            y = y * self.weight.view(1, -1, 1) + self.bias.view(1, -1, 1)
+        return y
+
+
+_NORMS = {"instance": MaskedInstanceNorm1d, "batch": MaskedBatchNorm1d}
+
+
+class _ConfigInit:
+    """`Cls.init(config=..., **overrides)` as the reference builds its modules (constructor.py:68-84):
+    merge a mapping / dataclass config with keyword overrides, drop keys the constructor does not
+    take (with a warning), refuse unset mandatory values."""
+
+    @classmethod
+    def init(cls, config=None, **parameters):
+        merged = {}
+        if config is not None:
+            if hasattr(config, "to_dict"):
+                merged.update(config.to_dict())
+            elif hasattr(config, "items"):
+                merged.update(dict(config.items()))
+            else:
+                merged.update({k: v for k, v in vars(config).items()})
+        merged.update(parameters)
+        merged = {k: v for k, v in merged.items() if not str(k).startswith("_")}
+        accepted = inspect.signature(cls.__init__).parameters
+        if "kwargs" not in accepted:
+            unknown = [k for k in merged if k not in accepted]
+            if unknown:
+                warnings.warn(f"The following params are incompatible with the {cls.__name__} constructor, "
+                              f"so they will be ignored: {unknown}.")
+                for k in unknown:
+                    merged.pop(k)
+        unset = [k for k, v in merged.items() if isinstance(v, str) and v == MISSING]
+        if unset:
+            raise RuntimeError(f"The following params are mandatory to set: {unset}")
+        return cls(**merged)
+
+
+# ----------------------------------------------------------------------------------------------
+# the fused log-likelihood as an autograd function
+# ----------------------------------------------------------------------------------------------
+def batch_diagonal_prior(text_lengths: Tensor, mel_lengths: Tensor, gamma: float = 0.1, threshold: float = 1e-4,
+                         max_text: int | None = None, max_mel: int | None = None) -> Tensor:
+    """Dense (B, T1max, T2max) prior, torch ops, for callers that want the tensor itself
+    (alignment.py:18-37).  The Aligner does NOT call this: the fused kernel evaluates the
+    same expression in registers."""
+    dev = text_lengths.device
+    t2 = int(text_lengths.max()) if max_text is None else max_text
+    t1 = int(mel_lengths.max()) if max_mel is None else max_mel
+    gt = torch.arange(t2, dtype=torch.float32, device=dev)[None, :] / text_lengths[:, None]
+    gm = torch.arange(t1, dtype=torch.float32, device=dev)[None, :] / mel_lengths[:, None]
+    g = gt[:, None, :] - gm[:, :, None]
+    prior = torch.exp(-g ** 2 / (2 * gamma ** 2))
+    valid = _length_mask(mel_lengths, t1)[:, :, None] & _length_mask(text_lengths, t2)[:, None, :]
+    prior = prior * valid
+    prior = prior / (prior.sum(dim=-1, keepdim=True) + 1e-5)
+    return prior.masked_fill(prior < threshold, 0.0)
+
+
+def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool):
+    dev = q.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    if q.dtype != k.dtype or q.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("Q and K must both be float32 or both bfloat16")
+    B, T1, D = q.shape
+    T2 = k.shape[1]
+    if k.shape[0] != B or k.shape[2] != D:
+        raise ValueError(f"shape mismatch: Q {tuple(q.shape)} vs K {tuple(k.shape)}")
+    q = q.contiguous()
+    k = k.contiguous()
+    tl = text_len.to(device=dev, dtype=torch.int64).contiguous()
+    ml = mel_len.to(device=dev, dtype=torch.int64).contiguous()
+    logits = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
+    soft = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
+    dt = _lib.ISP_DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+    with torch.cuda.device(dev):
+        rc = lib.isp_loglik_forward(q.data_ptr(), k.data_ptr(), dt, tl.data_ptr(), ml.data_ptr(), B, T1, T2, D,
+                                    float(scale), 1 if prior else 0, logits.data_ptr(), soft.data_ptr(), None, 0,
+                                    torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "isp_loglik_forward")
+    return soft, logits
+
+
+class _LogLikelihood(torch.autograd.Function):
+    """forward: the fused sm_100a kernel.  backward: composed from torch ops for now
+    (the fused backward is SURVEY.md section 8 f-1)."""
+
+    @staticmethod
+    def forward(ctx, q, k, text_len, mel_len, scale, prior):
+        soft, logits = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior)
+        ctx.save_for_backward(q, k, text_len, mel_len, soft)
+        ctx.scale, ctx.prior = scale, prior
+        return soft, logits
+
+    @staticmethod
+    def backward(ctx, g_soft, g_logits):
+        q, k, text_len, mel_len, soft = ctx.saved_tensors
+        qf, kf = q.float(), k.float()
+        g_total = torch.zeros_like(soft) if g_logits is None else g_logits.float().clone()
+        if g_soft is not None:
+            # attn_soft = softmax over valid text of attn_logits, times mask (alignment.py:201-206)
+            gs = g_soft.float()
+            g_total = g_total + soft * (gs - (gs * soft).sum(dim=2, keepdim=True))
+        if ctx.prior:
+            # attn_logits = S - logsumexp_all(S) + const (alignment.py:196)
+            s = ctx.scale * torch.matmul(qf, kf.transpose(1, 2))
+            d_s = g_total - torch.softmax(s, dim=2) * g_total.sum(dim=2, keepdim=True)
+        else:
+            d_s = g_total
+        d_s = d_s * ctx.scale
+        gq = torch.matmul(d_s, kf).to(q.dtype) if ctx.needs_input_grad[0] else None
+        gk = torch.matmul(d_s.transpose(1, 2), qf).to(k.dtype) if ctx.needs_input_grad[1] else None
+        return gq, gk, None, None, None, None
+
+
+def loglik_forward(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float | None = None,
+                   attention_prior: bool = True):
+    """(attn_soft, attn_logits) from encoded frames q (B, T1, D) and tokens k (B, T2, D);
+    rows of q / k past each utterance's length must be zero (the projections guarantee it)."""
+    scale = q.shape[-1] ** -0.5 if scale is None else scale
+    return _LogLikelihood.apply(q, k, text_len, mel_len, scale, attention_prior)
+
+
+# ----------------------------------------------------------------------------------------------
+# modules
+# ----------------------------------------------------------------------------------------------
+class ConvBlock1D(nn.Module):
+    """conv -> activation -> (masked) norm -> dropout, input masked first (alignment.py:40-83)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 1, stride: int = 1,
+                 padding: int | None = None, dilation: int = 1, bias: bool = True, activation: str = "relu",
+                 normalization: str | None = "batch", dropout_p: float | None = None):
+        super().__init__()
+        pad = int(dilation * (kernel_size - 1) / 2) if padding is None else padding
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=pad,
+                              dilation=dilation, bias=bias and normalization is None)
+        self.act = _ACTIVATIONS[str(getattr(activation, "value", activation))]()
+        self.norm = _NORMS[str(getattr(normalization, "value", normalization))](num_features=out_channels) \
+            if normalization is not None else None
+        # the reference crashes on dropout_p=None; None / 0 mean identity here
+        self.dropout = nn.Dropout(p=float(dropout_p)) if dropout_p else nn.Identity()
+
+    def forward(self, x: Tensor, input_mask: Tensor | None = None, output_mask: Tensor | None = None) -> Tensor:
+        if input_mask is not None:
+            x = x * input_mask
+        x = self.act(self.conv(x))
+        if self.norm is not None:
+            x = self.norm(x, mask=output_mask)
+        return self.dropout(x)
+
+    def forward_tokens_major(self, x: Tensor, input_mask: Tensor) -> Tensor:
+        """Same block for the pointwise, un-normalised last layer, emitting (B, T, C_out):
+        a 1x1 convolution is a matmul over channels, and K-major rows are what the GEMM loads."""
+        w = self.conv.weight[:, :, 0]
+        y = torch.matmul((x * input_mask).transpose(1, 2), w.t())
+        if self.conv.bias is not None:
+            y = y + self.conv.bias
+        return self.dropout(self.act(y))
+
+
+@dataclass
+class ConvAttentionConfig:
+    mel_dim: int = MISSING
+    text_dim: int = 512
+    attention_dim: int = 80
+    key_kernel_size: int = 3
+    query_kernel_size: int | Sequence[int] = (3, 3)
+    dropout: float = 0.0
+    normalization: str | None = "instance"
+    activation: str = "relu"
+
+    def to_dict(self):
+        return dict(self.__dict__)
+
+
+@dataclass
+class AlignerConfig(ConvAttentionConfig):
+    ...
+
+
+class ConvAttention(nn.Module, _ConfigInit):
+    def __init__(self, mel_dim: int, text_dim: int = 512, attention_dim: int = 80, key_kernel_size: int = 3,
+                 query_kernel_size: int | Sequence[int] = (3, 3), dropout: float = 0.0,
+                 normalization: str | None = "instance", activation: str = "relu", attention_prior: bool = True):
+        super().__init__()
+        self.mel_dim, self.text_dim = mel_dim, text_dim
+        self.scale = attention_dim ** -0.5
+        self.attention_prior = attention_prior
+        #: "auto": bf16 operands under autocast, fp32 operands (TF32 products) otherwise; or "fp32" / "bf16"
+        self.gemm_dtype = "auto"
+        drop = dropout if dropout and dropout > 0.0 else None
+        if isinstance(query_kernel_size, int):
+            query_kernel_size = [query_kernel_size] * 2
+
+        def stack(spec):
+            last = len(spec) - 1
+            return nn.ModuleList([
+                ConvBlock1D(cin, cout, kernel_size=ks, bias=False, activation=act,
+                            normalization=normalization if n < last else None, dropout_p=drop)
+                for n, (cin, cout, ks, act) in enumerate(spec)])
+
+        self.key_proj = stack([(text_dim, text_dim * 2, key_kernel_size, activation),
+                               (text_dim * 2, attention_dim, 1, "linear")])
+        self.query_proj = stack([(mel_dim, mel_dim * 2, query_kernel_size[0], activation),
+                                 (mel_dim * 2, mel_dim, query_kernel_size[1], activation),
+                                 (mel_dim, attention_dim, 1, "linear")])
+
+    @staticmethod
+    def _project(blocks, x: Tensor, mask: Tensor) -> Tensor:
+        for blk in blocks[:-1]:
+            x = blk(x, input_mask=mask, output_mask=mask)
+        last = blocks[-1]
+        if last.norm is None and last.conv.kernel_size == (1,):
+            return last.forward_tokens_major(x, mask)          # (B, T, D), zero on padded rows
+        return last(x, input_mask=mask, output_mask=mask).transpose(1, 2)
+
+    def encode(self, queries: Tensor, keys: Tensor, query_len: Tensor, key_len: Tensor):
+        """The two projection stacks (alignment.py:176-187) -> q (B, T1, D), k (B, T2, D)."""
+        keys = keys.transpose(1, 2) if keys.shape[1] != self.text_dim else keys
+        queries = queries.transpose(1, 2) if queries.shape[1] != self.mel_dim else queries
+        key_mask = _length_mask(key_len, keys.shape[2]).unsqueeze(1)
+        query_mask = _length_mask(query_len, queries.shape[2]).unsqueeze(1)
+        k = self._project(self.key_proj, keys, key_mask)
+        q = self._project(self.query_proj, queries, query_mask)
+        # keep the zero-padding contract of the kernel even when dropout / bias made pads non-zero
+        return q * query_mask.transpose(1, 2), k * key_mask.transpose(1, 2)
+
+    def forward(self, queries: Tensor, keys: Tensor, query_len: Tensor, key_len: Tensor):
+        """queries (B, mel_dim, T1) mel, keys (B, text_dim, T2) encoded text, lengths (B,)
+        -> (attn_soft, attn_logits), both (B, T1, T2) fp32 (alignment.py:159-208)."""
+        q, k = self.encode(queries, keys, query_len, key_len)
+        mode = self.gemm_dtype
+        if mode == "auto":
+            mode = "bf16" if torch.is_autocast_enabled() else "fp32"
+        if mode == "bf16":
+            q, k = q.to(torch.bfloat16), k.to(torch.bfloat16)
+        else:
+            q, k = q.float(), k.float()
+        return loglik_forward(q, k, key_len, query_len, self.scale, self.attention_prior)
+
+
+class AlignerOutput(NamedTuple):
+    attn_soft: Tensor
+    attn_logits: Tensor
+    attn_hard: Tensor
+    attn_hard_duration: Tensor
+
+
+class Aligner(nn.Module, _ConfigInit):
+    def __init__(self, mel_dim: int, text_dim: int = 512, attention_dim: int = 80, key_kernel_size: int = 3,
+                 query_kernel_size: int | Sequence[int] = (3, 3), dropout: float = 0.0,
+                 normalization: str | None = "instance", activation: str = "relu", attention_prior: bool = True):
+        super().__init__()
+        self.attention = ConvAttention(mel_dim=mel_dim, text_dim=text_dim, attention_dim=attention_dim,
+                                       key_kernel_size=key_kernel_size, query_kernel_size=query_kernel_size,
+                                       dropout=dropout, normalization=normalization, activation=activation,
+                                       attention_prior=attention_prior)
+
+    def forward(self, mel: Tensor, enc_text: Tensor, mel_len: Tensor, text_len: Tensor) -> AlignerOutput:
+        attn_soft, attn_logits = self.attention(queries=mel, keys=enc_text, query_len=mel_len, key_len=text_len)
+        attn_hard, duration = self._align(attn_logits, text_len, mel_len)
+        # every valid frame gets exactly one 1, so durations sum to mel_len by construction and the
+        # reference's print-and-patch check (alignment.py:278-282, a device->host sync) never fires
+        return AlignerOutput(attn_soft=attn_soft, attn_logits=attn_logits, attn_hard=attn_hard,
+                             attn_hard_duration=duration)
+
+    @staticmethod
+    @torch.no_grad()
+    def _align(attn_logits: Tensor, text_len: Tensor, mel_len: Tensor):
+        return mas_forward(attn_logits, text_len, mel_len, durations=True)
+
+    @torch.no_grad()
+    def binarize_attention_parallel(self, attn_logits: Tensor, text_len: Tensor, mel_len: Tensor) -> Tensor:
+        """MAS hard path, int16 (B, T1max, T2max); no gradient (alignment.py:291-301)."""
+        return self._align(attn_logits, text_len, mel_len)[0]
+
+    # the reference's two static routes, kept so external callers keep working; both run the kernel
+    @staticmethod
+    @torch.no_grad()
+    def cuda_binarize_attention_parallel(attn_logits: Tensor, text_len: Tensor, mel_len: Tensor) -> Tensor:
+        return mas_forward(attn_logits, text_len, mel_len, durations=False)[0]
+
+    @staticmethod
+    @torch.no_grad()
+    def cpu_binarize_attention_parallel(attn_logits: Tensor, text_len: Tensor, mel_len: Tensor) -> Tensor:
+        if not attn_logits.is_cuda:
+            raise _lib.IspError("there is no CPU MAS in this package: move attn_logits to a B200")
+        return mas_forward(attn_logits, text_len, mel_len, durations=False)[0]

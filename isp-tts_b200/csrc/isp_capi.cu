@@ -1,0 +1,83 @@
+// C ABI (include/isp_tts_b200.h): argument checks, error strings, dispatch.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "isp_internal.h"
+
+namespace isp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return int(e);
+}
+
+}  // namespace isp
+
+extern "C" {
+
+int isp_version(void) { return 100; }  // 0.1.0
+
+const char* isp_last_error(void) { return isp::g_err; }
+
+int isp_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return isp::cuda_fail(e, "cudaGetDevice");
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return isp::cuda_fail(e, "cudaDeviceGetAttribute");
+    if (major != 10) {
+        isp::set_error("device %d has compute capability %d.x; these kernels are built for sm_100a only", dev, major);
+        return ISP_ERR_DEVICE;
+    }
+    return ISP_OK;
+}
+
+size_t isp_mas_workspace_bytes(int B, int T1max, int T2max) { return isp::mas_workspace_bytes(B, T1max, T2max); }
+
+int isp_mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2, const int64_t* text_len,
+                    const int64_t* mel_len, int B, int T1max, int T2max, int16_t* attn_hard, int64_t* durations,
+                    void* ws, size_t ws_bytes, void* stream) {
+    return isp::mas_forward(logp, sB, sT1, sT2, text_len, mel_len, B, T1max, T2max, attn_hard, durations, ws,
+                            ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int isp_mas_status(const void* ws, void* stream) {
+    if (!ws) { isp::set_error("isp_mas_status: null workspace"); return -1; }
+    int v = -1;
+    cudaError_t e = cudaMemcpyAsync(&v, ws, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { isp::cuda_fail(e, "isp_mas_status"); return -1; }
+    return v;
+}
+
+size_t isp_loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype) {
+    return isp::loglik_workspace_bytes(B, T1max, T2max, D, dtype);
+}
+
+int isp_loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                       int B, int T1max, int T2max, int D, float scale, int attention_prior, float* attn_logits,
+                       float* attn_soft, void* ws, size_t ws_bytes, void* stream) {
+    return isp::loglik_forward(Q, K, dtype, text_len, mel_len, B, T1max, T2max, D, scale, attention_prior,
+                               attn_logits, attn_soft, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int isp_set_option(const char* key, int value) {
+    if (!key) return ISP_ERR_INVALID;
+    int prev = 0;
+    if (isp::mas_set_option(key, value, &prev) == 0) return prev;
+    if (isp::loglik_set_option(key, value, &prev) == 0) return prev;
+    isp::set_error("isp_set_option: unknown key '%s'", key);
+    return ISP_ERR_INVALID;
+}
+
+}  // extern "C"

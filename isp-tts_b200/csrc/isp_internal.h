@@ -1,0 +1,28 @@
+// Internal declarations shared by the kernels and the C-ABI layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/isp_tts_b200.h"
+
+namespace isp {
+
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+
+size_t mas_workspace_bytes(int B, int T1max, int T2max);
+int    mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
+                   const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                   int16_t* attn_hard, int64_t* durations, void* ws, size_t ws_bytes, cudaStream_t stream);
+int    mas_set_option(const char* key, int value, int* prev);
+
+size_t loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
+int    loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                      int B, int T1max, int T2max, int D, float scale, int attention_prior,
+                      float* attn_logits, float* attn_soft, void* ws, size_t ws_bytes, cudaStream_t stream);
+int    loglik_set_option(const char* key, int value, int* prev);
+
+}  // namespace isp

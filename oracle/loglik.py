@@ -29,7 +29,7 @@ def mask_from_lengths(lengths, max_len):
 
 
 def batch_diagonal_prior(text_lengths, mel_lengths, gamma=0.1, threshold=1e-4,
-                         t2max=None, t1max=None):
+                         t2max=None, t1max=None, return_unthresholded=False):
     """(B, T1max, T2max) fp32.  alignment.py:18-37."""
     tl = np.asarray(text_lengths)
     ml = np.asarray(mel_lengths)
@@ -43,7 +43,10 @@ def batch_diagonal_prior(text_lengths, mel_lengths, gamma=0.1, threshold=1e-4,
     prior[~np.broadcast_to(mask_from_lengths(tl, t2max)[:, None, :], prior.shape)] = 0.0  # :31
     prior[~mask_from_lengths(ml, t1max)] = 0.0                                    # :32
     prior = prior / (prior.sum(axis=-1, keepdims=True, dtype=f32) + f32(1e-5))    # :34
+    raw = prior
     prior = np.where(prior < f32(threshold), f32(0.0), prior).astype(f32)         # :35
+    if return_unthresholded:
+        return prior, raw
     return prior
 
 
@@ -73,9 +76,9 @@ def loglik(Q, K, text_len, mel_len, scale=None, attention_prior=True, return_par
     key_mask = mask_from_lengths(tl, T2)[:, None, :]               # :176
     query_mask = mask_from_lengths(ml, T1)[:, :, None]             # :177
     mask = query_mask & key_mask                                   # :178
-    prior = None
+    prior = prior_raw = None
     if attention_prior:
-        prior = batch_diagonal_prior(tl, ml, t2max=T2, t1max=T1)   # :195
+        prior, prior_raw = batch_diagonal_prior(tl, ml, t2max=T2, t1max=T1, return_unthresholded=True)   # :195
         attn = log_softmax(S, axis=2) + np.log(prior + PRIOR_EPS).astype(f32)  # :196
     else:
         attn = S
@@ -87,8 +90,17 @@ def loglik(Q, K, text_len, mel_len, scale=None, attention_prior=True, return_par
     soft = (e / e.sum(axis=2, keepdims=True, dtype=f32)).astype(f32)       # :203
     soft = (soft * mask).astype(f32)                               # :206
     if return_parts:
-        return soft, attn_logits, dict(S=S, prior=prior, mask=mask)
+        return soft, attn_logits, dict(S=S, prior=prior, prior_raw=prior_raw, mask=mask)
     return soft, attn_logits
+
+
+def threshold_ambiguous(prior_raw, threshold=1e-4, rel=2e-5):
+    """Cells whose normalised prior lies within `rel` of the hard threshold of alignment.py:35.
+    The reference zeroes a prior below 1e-4, so an implementation that differs from it by one
+    rounding in exp / sum can land on the other side there (its own CPU and CUDA builds do);
+    parity tests exclude these cells and bound how many there are."""
+    t = np.float32(threshold)
+    return np.abs(prior_raw - t) <= np.float32(rel) * t
 
 
 def durations_from_hard(attn_hard):

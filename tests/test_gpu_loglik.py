@@ -1,0 +1,150 @@
+"""GPU parity of the fused log-likelihood kernel (tcgen05 GEMM + epilogue) against the golden
+outputs of the reference's ConvAttention.forward and against the pinned numpy oracle.
+
+Tolerances (north star: "log-likelihood within 1e-3 relative in fp32, bf16 stated separately"):
+  fp32 operands (TF32 products, fp32 accumulate):  |d logits| <= 1e-3 * |logits| + 1e-4,  |d soft| <= 1e-3
+  bf16 operands:                                   |d logits| <= 5e-3 * |logits| + 2e-2,  |d soft| <= 2e-2
+Cells whose prior lies within 2e-5 (relative) of the reference's hard 1e-4 threshold
+(alignment.py:35) may land on either side; they are excluded and counted (must be < 0.1 %).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from isp_tts_b200 import _lib, synth
+from isp_tts_b200.alignment import loglik_forward
+from oracle import loglik as oll
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": dict(rel=1e-3, abs=1e-4, soft=1e-3), "bf16": dict(rel=5e-3, abs=2e-2, soft=2e-2)}
+
+
+def run(q, k, tl, ml, dev, dtype="fp32", prior=True):
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    qt = torch.from_numpy(q).to(dev).to(td)
+    kt = torch.from_numpy(k).to(dev).to(td)
+    soft, logits = loglik_forward(qt, kt, torch.from_numpy(np.asarray(tl)).to(dev),
+                                  torch.from_numpy(np.asarray(ml)).to(dev), attention_prior=prior)
+    torch.cuda.synchronize()
+    return soft.cpu().numpy(), logits.cpu().numpy()
+
+
+def compare(soft, logits, ref_soft, ref_logits, ambiguous, tol, what):
+    assert np.all(np.isfinite(logits)) and np.all(np.isfinite(soft)), what
+    ok = ~ambiguous
+    assert ambiguous.mean() < 1e-3, f"{what}: {ambiguous.sum()} cells on the prior threshold"
+    err = np.abs(logits - ref_logits)
+    bound = tol["rel"] * np.abs(ref_logits) + tol["abs"]
+    if not np.all(err[ok] <= bound[ok]):
+        bad = np.argwhere((err > bound) & ok)
+        b, i, j = bad[0]
+        raise AssertionError(f"{what}: {len(bad)} logits out of tolerance; first (b={b}, i={i}, j={j}) "
+                             f"cuda={logits[b, i, j]:.6f} ref={ref_logits[b, i, j]:.6f}; max err {err[ok].max():.3e}")
+    # a flipped cell changes its row's normaliser: compare soft on rows without ambiguous cells
+    rows_ok = ~ambiguous.any(axis=2, keepdims=True)
+    serr = np.abs(soft - ref_soft) * rows_ok
+    assert serr.max() <= tol["soft"], f"{what}: attn_soft max err {serr.max():.3e}"
+    return float(err[ok].max()), float(serr.max())
+
+
+@pytest.mark.parametrize("tag", ["small", "dim80", "dim128"])
+def test_scores_only(cuda_device, tag):
+    """The GEMM alone (debug option): scale * Q.K^T against fp64 numpy."""
+    g = golden(f"loglik_{tag}.npz")
+    _lib.set_option("loglik.debug_scores", 1)
+    try:
+        _, s = run(g["Q"], g["K"], g["text_len"], g["mel_len"], cuda_device)
+    finally:
+        _lib.set_option("loglik.debug_scores", 0)
+    ref = (g["Q"].astype(np.float64) @ g["K"].astype(np.float64).transpose(0, 2, 1)) * g["Q"].shape[2] ** -0.5
+    err = np.abs(s - ref)
+    assert err.max() < 2e-3 * max(1.0, np.abs(ref).max()), f"{tag}: max |dS| = {err.max():.3e} (|S| max {np.abs(ref).max():.3f})"
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["small", "dim80", "dim128"])
+def test_golden_reference_outputs(cuda_device, tag, dtype):
+    g = golden(f"loglik_{tag}.npz")
+    soft, logits = run(g["Q"], g["K"], g["text_len"], g["mel_len"], cuda_device, dtype)
+    _, _, parts = oll.loglik(g["Q"], g["K"], g["text_len"], g["mel_len"], return_parts=True)
+    amb = oll.threshold_ambiguous(parts["prior_raw"])
+    compare(soft, logits, g["attn_soft"], g["attn_logits"], amb, TOL[dtype], f"{tag}/{dtype}")
+    # structure: padded frames and padded tokens carry no soft mass, valid rows sum to 1
+    mask = parts["mask"]
+    assert np.all(soft[~np.broadcast_to(mask, soft.shape)] == 0)
+    rows = np.arange(soft.shape[1])[None, :] < g["mel_len"][:, None]
+    assert np.allclose(soft.sum(2)[rows], 1.0, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(6, 300, 100, 128), (5, 130, 201, 80), (3, 700, 256, 128), (2, 129, 8, 16)])
+def test_against_oracle(cuda_device, shape, dtype):
+    B, T1, T2, D = shape
+    tl, ml = synth.lengths(B, T2, T1, True, 77 + T2)
+    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, 99 + T1)
+    if dtype == "bf16":   # compare at the operands' precision: round first, then both sides see the same numbers
+        q = torch.from_numpy(q).to(torch.bfloat16).float().numpy()
+        k = torch.from_numpy(k).to(torch.bfloat16).float().numpy()
+    soft, logits = run(q, k, tl, ml, cuda_device, dtype)
+    rs, rl, parts = oll.loglik(q, k, tl, ml, return_parts=True)
+    amb = oll.threshold_ambiguous(parts["prior_raw"])
+    tol = TOL["fp32"] if dtype == "fp32" else dict(rel=1e-3, abs=1e-4, soft=1e-3)   # bf16 inputs are exact products
+    compare(soft, logits, rs, rl, amb, tol, f"{shape}/{dtype}")
+
+
+def test_long_text_two_accumulator_chunks(cuda_device):
+    """256 < T2max <= 512 uses all 512 TMEM columns (bf16 operands)."""
+    B, T1, T2, D = 2, 260, 512, 128
+    tl, ml = np.array([512, 300]), np.array([260, 140])
+    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, 5)
+    q = torch.from_numpy(q).to(torch.bfloat16).float().numpy()
+    k = torch.from_numpy(k).to(torch.bfloat16).float().numpy()
+    soft, logits = run(q, k, tl, ml, cuda_device, "bf16")
+    rs, rl, parts = oll.loglik(q, k, tl, ml, return_parts=True)
+    compare(soft, logits, rs, rl, oll.threshold_ambiguous(parts["prior_raw"]), dict(rel=1e-3, abs=1e-4, soft=1e-3), "T2=512")
+
+
+def test_without_prior(cuda_device):
+    g = golden("loglik_dim80.npz")
+    soft, logits = run(g["Q"], g["K"], g["text_len"], g["mel_len"], cuda_device, prior=False)
+    rs, rl = oll.loglik(g["Q"], g["K"], g["text_len"], g["mel_len"], attention_prior=False)
+    assert np.abs(logits - rl).max() < 2e-3 and np.abs(soft - rs).max() < 1e-3
+
+
+def test_unsupported_shapes_raise(cuda_device):
+    z = lambda *s: torch.zeros(*s, device=cuda_device)
+    one = torch.ones(1, dtype=torch.int64, device=cuda_device)
+    with pytest.raises(_lib.IspError):
+        loglik_forward(z(1, 8, 12), z(1, 8, 12), one, one)            # D % 8 != 0
+    with pytest.raises(_lib.IspError):
+        loglik_forward(z(1, 8, 16), z(1, 513, 16), one, one)          # T2max > 512
+    with pytest.raises(_lib.IspError):
+        loglik_forward(torch.zeros(1, 8, 16), torch.zeros(1, 8, 16), one.cpu(), one.cpu())   # CPU tensors
+
+
+def test_backward_matches_torch_autograd(cuda_device):
+    """Gradients of (attn_soft, attn_logits) w.r.t. q, k against a plain torch restatement."""
+    B, T1, T2, D = 3, 70, 24, 32
+    tl, ml = synth.lengths(B, T2, T1, True, 3)
+    qn, kn = synth.encoded_pair(B, T1, T2, D, tl, ml, 4)
+    tlt, mlt = torch.from_numpy(tl).to(cuda_device), torch.from_numpy(ml).to(cuda_device)
+    q = torch.from_numpy(qn).to(cuda_device).requires_grad_(True)
+    k = torch.from_numpy(kn).to(cuda_device).requires_grad_(True)
+    soft, logits = loglik_forward(q, k, tlt, mlt)
+    w1 = torch.randn_like(soft); w2 = torch.randn_like(logits)
+    (soft * w1).sum().add((logits * w2).sum()).backward()
+    gq, gk = q.grad.clone(), k.grad.clone()
+
+    q2 = q.detach().clone().requires_grad_(True); k2 = k.detach().clone().requires_grad_(True)
+    from isp_tts_b200.alignment import batch_diagonal_prior
+    s = D ** -0.5 * torch.matmul(q2, k2.transpose(1, 2))
+    prior = batch_diagonal_prior(tlt, mlt, max_text=T2, max_mel=T1)
+    lg = torch.log_softmax(s, dim=2) + torch.log(prior + 1e-6)
+    km = (torch.arange(T2, device=cuda_device)[None] < tlt[:, None])[:, None, :]
+    qm = (torch.arange(T1, device=cuda_device)[None] < mlt[:, None])[:, :, None]
+    sf = torch.softmax(lg.masked_fill(~km, -3.4028234663852886e38), dim=2) * (km & qm)
+    (sf * w1).sum().add((lg * w2).sum()).backward()
+    assert torch.allclose(gq, q2.grad, rtol=2e-3, atol=2e-3), (gq - q2.grad).abs().max()
+    assert torch.allclose(gk, k2.grad, rtol=2e-3, atol=2e-3), (gk - k2.grad).abs().max()

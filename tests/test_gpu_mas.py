@@ -1,0 +1,192 @@
+"""GPU parity of the MAS kernel: CUDA path (through the C ABI) vs the pinned CPU oracle and
+the committed golden vectors.  Everything here is bit-exact: int16 path, int64 durations."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from isp_tts_b200 import _lib, synth
+from isp_tts_b200.mas import b_mas, cuda_b_mas, mas_forward
+from oracle import mas as omas
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(x, tl, ml, dev, **kw):
+    xt = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    hard, dur = mas_forward(xt, torch.from_numpy(np.asarray(tl)), torch.from_numpy(np.asarray(ml)), **kw)
+    torch.cuda.synchronize()
+    return hard.cpu().numpy(), dur.cpu().numpy(), xt
+
+
+def assert_same(hard, dur, ref_hard, ref_dur, what=""):
+    if not np.array_equal(hard, ref_hard):
+        bad = np.argwhere(hard != ref_hard)
+        b = bad[0][0]
+        rows = np.unique(bad[bad[:, 0] == b][:, 1])
+        raise AssertionError(f"{what}: path differs in {len(np.unique(bad[:, 0]))} utterance(s); first b={b}, "
+                             f"{len(rows)} rows, first rows {rows[:8].tolist()}; cuda cols "
+                             f"{hard[b, rows[:8]].argmax(1).tolist()} vs oracle {ref_hard[b, rows[:8]].argmax(1).tolist()}; "
+                             f"ones per utt cuda={hard[b].sum()} oracle={ref_hard[b].sum()}")
+    assert np.array_equal(dur, ref_dur), f"{what}: durations differ"
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    yield
+    _lib.set_option("mas.cols_per_lane", 0)
+    _lib.set_option("mas.ring_rows", 0)
+
+
+def test_known_answers(cuda_device):
+    g = golden("mas_kat.npz")
+    hard, dur, _ = run_cuda(g["a12_x"][None], [3], [5], cuda_device)
+    assert np.array_equal(hard[0], g["a12_hard"])
+    assert dur[0].tolist() == [1, 2, 2]
+    for name in ["zeros_10x4", "zeros_3x6", "zeros_1x3", "zeros_5x1", "zeros_1x1", "zeros_7x7"]:
+        ref = g[name + "_hard"]
+        n, m = ref.shape
+        hard, dur, _ = run_cuda(np.zeros((1, n, m), np.float32), [m], [n], cuda_device)
+        assert np.array_equal(hard[0], ref), name
+        assert np.array_equal(dur[0], ref.sum(0)), name
+
+
+@pytest.mark.parametrize("cols", [0, 4, 8])
+def test_cfg1_single_utterance(cuda_device, cols):
+    """BASELINE.json configs[0]: 80 tokens x 400 frames, reference maximum path, bit-exact."""
+    _lib.set_option("mas.cols_per_lane", cols)
+    g = golden("mas_cfg1.npz")
+    hard, dur, xt = run_cuda(g["x"], g["text_len"], g["mel_len"], cuda_device)
+    assert np.array_equal(omas.path_from_hard(hard, g["mel_len"]), g["path"])
+    assert np.array_equal(dur, g["durations"])
+    assert np.array_equal(xt.cpu().numpy(), g["x"])          # input untouched
+
+
+@pytest.mark.parametrize("cols", [4, 8])
+def test_ragged_batch_with_ties(cuda_device, cols):
+    _lib.set_option("mas.cols_per_lane", cols)
+    g = golden("mas_ragged_ties.npz")
+    hard, dur, _ = run_cuda(g["x"], g["text_len"], g["mel_len"], cuda_device)
+    assert_same(hard, dur, g["hard"], g["hard"].sum(axis=1, dtype=np.int64), "ragged_ties")
+    assert np.array_equal(dur.sum(1), g["mel_len"])
+
+
+@pytest.mark.parametrize("cols", [4, 8])
+@pytest.mark.parametrize("tag", ["cfg2_noise", "cfg2_ties", "odd_shapes", "wide", "long"])
+def test_seeded_golden(cuda_device, tag, cols):
+    _lib.set_option("mas.cols_per_lane", cols)
+    g = golden(f"mas_seeded_{tag}.npz")
+    B, T1, T2 = int(g["B"]), int(g["T1"]), int(g["T2"])
+    x = synth.noise_logits(B, T1, T2, int(g["seed"]), quantize=float(g["quantize"]))
+    hard, dur, _ = run_cuda(x, g["text_len"], g["mel_len"], cuda_device)
+    assert np.array_equal(omas.path_from_hard(hard, g["mel_len"]), g["path"]), tag
+    assert np.array_equal(dur, g["durations"]), tag
+    # nothing outside each window
+    for b in range(B):
+        assert hard[b, int(g["mel_len"][b]):].sum() == 0 and hard[b, :, int(g["text_len"][b]):].sum() == 0
+
+
+@pytest.mark.parametrize("ring", [8, 16, 24])
+def test_small_ring_wraparound(cuda_device, ring):
+    """Few rows in flight: every ring stage is reused many times."""
+    _lib.set_option("mas.ring_rows", ring)
+    x = synth.noise_logits(9, 257, 130, 5, quantize=0.25)
+    tl, ml = synth.lengths(9, 130, 257, True, 5)
+    for cols in (4, 8):
+        _lib.set_option("mas.cols_per_lane", cols)
+        hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+        rh, rd = omas.b_mas_with_durations(x, tl, ml)
+        assert_same(hard, dur, rh, rd, f"ring={ring} cols={cols}")
+
+
+def test_full_size_cfg3_against_oracle(cuda_device):
+    """BASELINE.json configs[2]: batch 256 ragged, <=200 x <=1000 (the bench workload)."""
+    w = synth.WORKLOADS["cfg3"]
+    tl, ml = synth.workload_lengths(w)
+    x = synth.noise_logits(w.batch, w.t1max, w.t2max, w.seed, quantize=0.125)
+    hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, "cfg3")
+    # size-independent properties
+    assert np.array_equal(hard.sum(axis=2)[np.arange(w.t1max)[None] < ml[:, None]], np.ones(int(ml.sum()), np.int64))
+    assert np.array_equal(dur.sum(1), ml)
+    p = omas.path_from_hard(hard, ml)
+    for b in range(w.batch):
+        pb = p[b, :ml[b]].astype(np.int64)
+        d = np.diff(pb)
+        assert pb[-1] == tl[b] - 1 and np.all((d == 0) | (d == 1))
+
+
+def test_full_size_cfg4_long_form(cuda_device):
+    """BASELINE.json configs[3]: 512 tokens x 4096 frames, batch 16 (bits spill to the workspace)."""
+    w = synth.WORKLOADS["cfg4"]
+    tl, ml = synth.workload_lengths(w)
+    x = synth.noise_logits(w.batch, w.t1max, w.t2max, w.seed)
+    for cols in (4, 8):
+        _lib.set_option("mas.cols_per_lane", cols)
+        hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+        rh, rd = omas.b_mas_with_durations(x, tl, ml)
+        assert_same(hard, dur, rh, rd, f"cfg4 cols={cols}")
+
+
+def test_maximum_width(cuda_device):
+    T2 = 2048
+    x = synth.noise_logits(2, 300, T2, 11, quantize=0.5)
+    tl, ml = np.array([2048, 1500]), np.array([300, 211])
+    hard, dur, _ = run_cuda(x, tl, ml, cuda_device)       # text longer than mel: pure diagonal tail
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, "T2=2048")
+    with pytest.raises(_lib.IspError):
+        mas_forward(torch.zeros(1, 4, 2049, device=cuda_device), torch.tensor([2049]), torch.tensor([4]))
+
+
+def test_unaligned_and_strided_inputs(cuda_device):
+    """Rows that are not 16 B aligned take the non-TMA producer path; padded row strides too."""
+    rs = np.random.RandomState(3)
+    for (B, T1, T2) in [(3, 50, 33), (2, 64, 7), (4, 31, 1), (2, 1, 9)]:
+        x = (np.rint(rs.standard_normal((B, T1, T2)) * 4) / 4).astype(np.float32)
+        tl = rs.randint(1, T2 + 1, size=B); ml = rs.randint(1, T1 + 1, size=B)
+        tl[0], ml[0] = T2, T1
+        hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+        rh, rd = omas.b_mas_with_durations(x, tl, ml)
+        assert_same(hard, dur, rh, rd, f"shape {(B, T1, T2)}")
+    # a strided view: row stride 40 floats for 36 columns, base offset 4 B off alignment
+    buf = torch.zeros(3 * 20 * 40 + 1, device=cuda_device)
+    x = (np.rint(rs.standard_normal((3, 20, 36)) * 2) / 2).astype(np.float32)
+    view = buf[1:].view(3, 20, 40)[:, :, :36]
+    view.copy_(torch.from_numpy(x))
+    tl, ml = np.array([36, 10, 22]), np.array([20, 20, 5])
+    hard, dur = mas_forward(view, torch.from_numpy(tl), torch.from_numpy(ml))
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard.cpu().numpy(), dur.cpu().numpy(), rh, rd, "strided view")
+
+
+def test_reference_entry_points(cuda_device):
+    """b_mas (numpy in/out) and cuda_b_mas[grid, block](...) keep the reference call shapes."""
+    g = golden("mas_ragged_ties.npz")
+    out = b_mas(g["x"].copy(), g["text_len"], g["mel_len"])                  # mas.py:30
+    assert isinstance(out, np.ndarray) and out.dtype == np.int16 and np.array_equal(out, g["hard"])
+    # alignment.py:321-331, verbatim apart from the import
+    attn_logits = torch.from_numpy(g["x"]).to(cuda_device)
+    text_len = torch.from_numpy(g["text_len"]).to(cuda_device)
+    mel_len = torch.from_numpy(g["mel_len"]).to(cuda_device)
+    log_p = attn_logits.clone().detach()
+    attn_out = torch.zeros_like(attn_logits, dtype=torch.int16)
+    prev_log_p = torch.zeros_like(attn_logits)
+    prev_ind = torch.zeros_like(attn_logits, dtype=torch.int16)
+    cuda_b_mas[(max(64, attn_logits.shape[0]), 1), (1, 256)](log_p, prev_log_p, prev_ind, attn_out, text_len, mel_len)
+    assert np.array_equal(attn_out.cpu().numpy(), g["hard"])
+    assert torch.equal(log_p, attn_logits)
+
+
+def test_out_of_contract_lengths_are_reported(cuda_device):
+    x = torch.zeros(3, 8, 5, device=cuda_device)
+    with pytest.raises(_lib.IspError):
+        mas_forward(x, torch.tensor([5, 9, 2]), torch.tensor([8, 8, 0]), check_lengths=True)
+    hard, dur = mas_forward(x, torch.tensor([5, 4, 2]), torch.tensor([8, 8, 3]), check_lengths=True)
+    assert dur.sum(1).tolist() == [8, 8, 3]
+
+
+def test_cpu_tensor_is_rejected():
+    with pytest.raises(_lib.IspError):
+        mas_forward(torch.zeros(1, 4, 4), torch.tensor([4]), torch.tensor([4]))
