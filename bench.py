@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the Aligner hot path (log-likelihood GEMM+epilogue -> MAS -> durations).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one synthetic LJSpeech-shaped batch per GPU
+(default workload cfg3 = BASELINE.json configs[2], the batch-256 ragged configuration the
+north-star target is quoted on).  Rank 0 prints ONE JSON line.  Under torchrun every rank
+owns its own batch (sharded by utterance, no collective on the data path): weak scaling.
+
+Keys beyond the base contract:
+  roofline      the dominant kernel of the step, timed live with CUDA events
+  kernels       per-kernel time / algorithmic bytes / fraction of the measured HBM peak
+  cpu_baseline  the oracle port (torch-CPU log-likelihood + C/OpenMP MAS) on a bounded sample
+  e2e           same metric through the public API with pinned HOST buffers (H2D + D2H timed)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aligned utterances/sec"
+UNIT = "utterances/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 0.0))), "measured"
+    return 6650.0, 1590.0, "fallback"      # /opt/skills/guides/B200_PROFILING.md
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work per launch (restated in DESIGN.md)
+# ------------------------------------------------------------------------------------------
+def mas_bytes(text_len, mel_len, B, T1, T2):
+    valid = int((text_len * mel_len).sum())
+    return 4 * valid + 2 * B * T1 * T2 + 8 * B * T2 + 16 * B
+
+
+def loglik_bytes(B, T1, T2, D, elem):
+    return elem * D * B * (T1 + T2) + 8 * B * T1 * T2
+
+
+def loglik_flops(B, T1, T2, D):
+    return 2 * D * B * T1 * T2
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_step(q, k, tl, ml, scale):
+    """One hot-path pass on the CPU: reference op sequence in torch-CPU + the C/OpenMP MAS."""
+    import torch
+    from oracle import loglik_torch as olt
+    from oracle import mas as omas
+    soft, logits = olt.loglik(q, k, tl, ml, scale)
+    hard, dur = omas.b_mas_with_durations(logits.numpy(), tl.numpy(), ml.numpy())
+    return dur
+
+
+def cpu_baseline(w, sample_utts, reps, warm=1):
+    import torch
+    from isp_tts_b200 import synth
+    from oracle import mas as omas
+    tl, ml = synth.workload_lengths(w)
+    n = min(sample_utts, w.batch)
+    tl, ml = tl[:n].copy(), ml[:n].copy()
+    q, k = synth.encoded_pair(n, w.t1max, w.t2max, w.dim, tl, ml, w.seed + 1)
+    qt, kt, tlt, mlt = torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(tl), torch.from_numpy(ml)
+    scale = w.dim ** -0.5
+    for _ in range(warm):
+        cpu_step(qt, kt, tlt, mlt, scale)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(qt, kt, tlt, mlt, scale)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    cores = max(torch.get_num_threads(), omas.num_threads())
+    return {
+        "value": n / best, "unit": UNIT, "cores": int(cores), "kind": "port",
+        "sample": f"first {n} of {w.batch} utterances of {w.name}; fp32; best of {reps} "
+                  f"(median {n / float(np.median(times)):.1f}); torch-CPU log-likelihood ops "
+                  f"(alignment.py:189-208 sequence) + C/OpenMP MAS (oracle/mas_oracle.c)",
+        "valid_cells_per_s": float((tl * ml).sum()) / best,
+        "ms_per_sample": best * 1e3,
+    }, times
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each step is a bounded sample of the workload so that K+W steps end within minutes
+    sample = min(w.batch, 32)
+    base, times = cpu_baseline(w, sample, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    med = float(np.median(times))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": sample / med, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "batch_per_gpu": w.batch, "t_text_max": w.t2max, "t_mel_max": w.t1max,
+                   "attention_dim": w.dim, "step": f"CPU port on a {sample}-utterance sample per step"},
+        "cpu_baseline": {"value": sample / med, "unit": UNIT, "cores": base["cores"], "kind": "port",
+                         "sample": base["sample"]},
+        "e2e": {"value": sample / med, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from isp_tts_b200 import synth
+    from isp_tts_b200.alignment import _loglik_cuda
+    from isp_tts_b200.mas import mas_forward
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    if args.mas_cols or args.mas_ring or args.mas_producer:
+        from isp_tts_b200 import _lib
+        _lib.set_option("mas.cols_per_lane", args.mas_cols)
+        _lib.set_option("mas.ring_rows", args.mas_ring)
+        _lib.set_option("mas.producer", args.mas_producer)
+    gemm_dtype = torch.bfloat16 if args.gemm == "bf16" else torch.float32
+    elem = 2 if args.gemm == "bf16" else 4
+    B, T1, T2, D = w.batch, w.t1max, w.t2max, w.dim
+    # every rank owns a different batch of the same law (utterance sharding, weak scaling)
+    tl, ml = synth.lengths(B, T2, T1, w.ragged, w.seed + 1000 * rank)
+    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, w.seed + 1 + 1000 * rank)
+    scale = D ** -0.5
+    q_host = torch.from_numpy(q).to(gemm_dtype).pin_memory()
+    k_host = torch.from_numpy(k).to(gemm_dtype).pin_memory()
+    tl_host, ml_host = torch.from_numpy(tl).pin_memory(), torch.from_numpy(ml).pin_memory()
+    q_dev, k_dev = q_host.to(dev), k_host.to(dev)
+    tl_dev, ml_dev = tl_host.to(dev), ml_host.to(dev)
+    dur_host = torch.empty((B, T2), dtype=torch.int64).pin_memory()
+
+    def step_resident(events=None):
+        if events is not None:
+            events[0].record()
+        soft, logits = _loglik_cuda(q_dev, k_dev, tl_dev, ml_dev, scale, True)
+        if events is not None:
+            events[1].record()
+        hard, dur = mas_forward(logits, tl_dev, ml_dev)
+        if events is not None:
+            events[2].record()
+        return dur
+
+    qd2, kd2 = torch.empty_like(q_dev), torch.empty_like(k_dev)
+    tld2, mld2 = torch.empty_like(tl_dev), torch.empty_like(ml_dev)
+
+    def step_e2e():
+        # public API, host buffers: H2D of this step's inputs, hot path, D2H of the durations
+        qd2.copy_(q_host, non_blocking=True)
+        kd2.copy_(k_host, non_blocking=True)
+        tld2.copy_(tl_host, non_blocking=True)
+        mld2.copy_(ml_host, non_blocking=True)
+        soft, logits = _loglik_cuda(qd2, kd2, tld2, mld2, scale, True)
+        hard, dur = mas_forward(logits, tld2, mld2)
+        dur_host.copy_(dur, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- resident-input timing (value) --------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        start.record()
+        for s in range(args.steps):
+            step_resident(evs[s])
+        end.record()
+        barrier()
+    total_ms = max_over_ranks(start.elapsed_time(end))
+    t_loglik = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    t_mas = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+
+    # ---- end-to-end timing through host buffers (e2e) -----------------------------------
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk2:
+        barrier()
+        s2.record()
+        for _ in range(args.steps):
+            step_e2e()
+        e2.record()
+        barrier()
+    e2e_ms = max_over_ranks(s2.elapsed_time(e2))
+    # durations must be what the resident path produced
+    ref_dur = step_resident().cpu()
+    torch.cuda.synchronize()
+    if not torch.equal(ref_dur, dur_host):
+        raise RuntimeError("e2e durations differ from the resident-input run")
+    if int(dur_host.sum()) != int(ml.sum()):
+        raise RuntimeError("durations do not sum to the mel lengths")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tf_peak, which = load_peaks()
+    by_mas = mas_bytes(tl, ml, B, T1, T2)
+    by_ll = loglik_bytes(B, T1, T2, D, elem)
+    fl_ll = loglik_flops(B, T1, T2, D)
+    kern = {
+        "isp_loglik (tcgen05 GEMM + fused epilogue)": {
+            "ms": t_loglik, "algorithmic_bytes": by_ll, "gbs": by_ll / t_loglik / 1e6, "hbm_frac": by_ll / t_loglik / 1e6 / hbm_peak,
+            "tflops": fl_ll / t_loglik / 1e9, "tensor_frac": fl_ll / t_loglik / 1e9 / tf_peak},
+        "isp_mas (wavefront DP + backtrack + durations)": {
+            "ms": t_mas, "algorithmic_bytes": by_mas, "gbs": by_mas / t_mas / 1e6, "hbm_frac": by_mas / t_mas / 1e6 / hbm_peak},
+    }
+    dom = max(kern, key=lambda n: kern[n]["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # per-launch DRAM bytes from the committed ncu capture
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(w.name.split(":")[0], {}).get(dom.split(" ")[0])
+        except Exception:
+            traffic = None
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kern[dom]["hbm_frac"], "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)"}
+
+    n_cpu = min(B, 32)
+    cpu, _ = cpu_baseline(w, n_cpu, reps=3)
+
+    utts = world * B * args.steps
+    valid_cells = float((tl * ml).sum()) * world * args.steps
+    h2d = q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size() + 16 * B
+    out = {
+        "metric": METRIC, "value": utts / (total_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 GEMM operands; f32 accumulate, epilogue and MAS" if elem == 2 else "tf32 GEMM products; f32 elsewhere",
+        "data": "synthetic",
+        "config": {"workload": w.name, "batch_per_gpu": B, "t_text_max": T2, "t_mel_max": T1, "attention_dim": D,
+                   "ragged": w.ragged, "valid_cells_per_batch": int((tl * ml).sum()), "padded_cells_per_batch": B * T1 * T2,
+                   "sharding": f"by utterance, {world} rank(s), no collective on the data path",
+                   "l2": "per-step working set (operands + 3 dense outputs) = %.0f MB > 126 MB L2; no explicit flush" % (
+                       (by_ll + 2 * B * T1 * T2) / 1e6)},
+        "valid_cells_per_s": valid_cells / (total_ms / 1e3),
+        "padded_cells_per_s": world * B * T1 * T2 * args.steps / (total_ms / 1e3),
+        "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
+        "e2e": {"value": utts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(dur_host.numel() * 8), "ms_per_step": e2e_ms / args.steps,
+                "api": "isp_loglik_forward + isp_mas_forward through isp_tts_b200 (pinned host Q, K, lengths in; durations out)"},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mas-cols", type=int, default=0, help="tuning: MAS columns per lane (4|8), 0 = heuristic")
+    ap.add_argument("--mas-ring", type=int, default=0, help="tuning: MAS logit rows in flight, 0 = heuristic")
+    ap.add_argument("--mas-producer", type=int, default=0, help="tuning/debug: MAS producer mode (see isp_mas.cu)")
+    args = ap.parse_args()
+    from isp_tts_b200 import synth
+    w = synth.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,30 @@ ISP_DEVINL uint64_t policy_evict_first() {
     return p;
 }
 
+// ---- Ampere-style async copy (LDGSTS), 16 B per lane, L2 only, completion on an mbarrier ----
+ISP_DEVINL void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+ISP_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// block until at most `n` of this thread's committed groups are still pending (n <= 7)
+ISP_DEVINL void cp_async_wait_pending(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+// arrives on `bar` once all cp.async issued so far by this thread have landed; does not
+// add to the pending count, so the barrier's init count must include one arrival per lane
+ISP_DEVINL void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- CTA-scope acquire/release on shared words (strip-to-strip progress flags) ----
 ISP_DEVINL void st_release_shared(int* p, int v) {
     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");

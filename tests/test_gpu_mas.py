@@ -130,14 +130,14 @@ def test_full_size_cfg4_long_form(cuda_device):
 
 
 def test_maximum_width(cuda_device):
-    T2 = 2048
+    T2 = 1024                                             # ISP_MAS_MAX_T2
     x = synth.noise_logits(2, 300, T2, 11, quantize=0.5)
-    tl, ml = np.array([2048, 1500]), np.array([300, 211])
+    tl, ml = np.array([1024, 700]), np.array([300, 211])
     hard, dur, _ = run_cuda(x, tl, ml, cuda_device)       # text longer than mel: pure diagonal tail
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
-    assert_same(hard, dur, rh, rd, "T2=2048")
+    assert_same(hard, dur, rh, rd, "T2=1024")
     with pytest.raises(_lib.IspError):
-        mas_forward(torch.zeros(1, 4, 2049, device=cuda_device), torch.tensor([2049]), torch.tensor([4]))
+        mas_forward(torch.zeros(1, 4, 1025, device=cuda_device), torch.tensor([1025]), torch.tensor([4]))
 
 
 def test_unaligned_and_strided_inputs(cuda_device):
