@@ -15,6 +15,7 @@ _LAZY = {
     "ConvAttention": "alignment", "ConvAttentionConfig": "alignment", "ConvBlock1D": "alignment",
     "batch_diagonal_prior": "alignment", "loglik_forward": "alignment",
     "b_mas": "mas", "cuda_b_mas": "mas", "mas_forward": "mas", "mas_durations": "mas",
+    "gather_durations": "sharding", "shard_bounds": "sharding", "balanced_assignment": "sharding",
 }
 
 
