@@ -199,11 +199,10 @@ def run_ours(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    if args.mas_cols or args.mas_ring or args.mas_producer:
+    if args.mas_ring or args.mas_slots:
         from isp_tts_b200 import _lib
-        _lib.set_option("mas.cols_per_lane", args.mas_cols)
         _lib.set_option("mas.ring_rows", args.mas_ring)
-        _lib.set_option("mas.producer", args.mas_producer)
+        _lib.set_option("mas.slots", args.mas_slots)
     gemm_dtype = torch.bfloat16 if args.gemm == "bf16" else torch.float32
     elem = 2 if args.gemm == "bf16" else 4
     B, T1, T2, D = w.batch, w.t1max, w.t2max, w.dim
@@ -358,9 +357,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--mas-cols", type=int, default=0, help="tuning: MAS columns per lane (4|8), 0 = heuristic")
     ap.add_argument("--mas-ring", type=int, default=0, help="tuning: MAS logit rows in flight, 0 = heuristic")
-    ap.add_argument("--mas-producer", type=int, default=0, help="tuning/debug: MAS producer mode (see isp_mas.cu)")
+    ap.add_argument("--mas-slots", type=int, default=0, help="tuning: utterances per CTA (1|2), 0 = heuristic")
     args = ap.parse_args()
     from isp_tts_b200 import synth
     w = synth.WORKLOADS[args.workload]

@@ -86,7 +86,7 @@ def test_seeded_golden(cuda_device, tag, cols):
         assert hard[b, int(g["mel_len"][b]):].sum() == 0 and hard[b, :, int(g["text_len"][b]):].sum() == 0
 
 
-@pytest.mark.parametrize("ring", [8, 16, 24])
+@pytest.mark.parametrize("ring", [48, 56, 80])
 def test_small_ring_wraparound(cuda_device, ring):
     """Few rows in flight: every ring stage is reused many times."""
     _lib.set_option("mas.ring_rows", ring)
