@@ -44,7 +44,7 @@ extern "C" {
 #define ISP_DTYPE_F32  0          /* fp32 in memory, TF32 tensor-core products, fp32 accumulate */
 #define ISP_DTYPE_BF16 1          /* bf16 in memory, fp32 accumulate */
 
-#define ISP_MAS_MAX_T2   1024     /* text tokens per utterance the MAS kernel covers */
+#define ISP_MAS_MAX_T2   640      /* text tokens per utterance the MAS kernel covers */
 #define ISP_LOGLIK_MAX_T2 512     /* text tokens per utterance the fused GEMM covers (TMEM columns) */
 #define ISP_LOGLIK_MAX_D  256     /* attention_dim */
 

@@ -65,7 +65,7 @@ def check(rc: int, what: str):
 
 def set_option(key: str, value: int) -> int:
     rc = load().isp_set_option(key.encode(), int(value))
-    if rc == -1 and key not in ("mas.cols_per_lane", "mas.ring_rows", "mas.slots", "mas.dbg", "loglik.debug_scores"):
+    if rc == -1 and key not in ("mas.cols_per_lane", "mas.ring_rows", "mas.slots", "mas.dbg", "mas.bits_global", "mas.no_tma", "loglik.debug_scores"):
         raise IspError(f"unknown option {key!r}")
     return rc
 

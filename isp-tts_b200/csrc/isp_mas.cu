@@ -9,45 +9,50 @@
 // Shape of the computation.  Q[i][j] = x[i][j] + max(Q[i-1][j-1], Q[i-1][j]) depends on
 // row i-1 only: the text axis is parallel, the frame axis is a serial chain of T1 steps, and
 // the time of a batch is the time of its longest chain unless HBM saturates first.  The
-// kernel is therefore built around the latency of ONE row step:
+// kernel is therefore built around the latency of ONE row step, and everything that is not
+// arithmetic of that step is moved off the warp that runs the chain (measured costs behind
+// these choices: tools/ubench/chain.cu, tools/ubench/sync.cu):
 //
 //   * One "slot" = one utterance in flight.  A CTA holds 1 or 2 slots; a slot is NS strip
-//     warps (32*C text columns each; C = 4 or 8 columns per lane) + one filler warp.  Strip warps get the lowest warp ids,
-//     so the strips of co-resident utterances sit on different SM sub-partitions and never
-//     compete for an issue port.
-//   * Inside a strip warp the wavefront is skewed across LANES: lane l owns C consecutive
+//     warps (128 text columns each, 4 per lane), NS loader warps and one filler warp.  Strip
+//     warps get the lowest warp ids, so the strips of co-resident utterances sit on different
+//     SM sub-partitions.
+//   * Inside a strip warp the wavefront is skewed across LANES: lane l owns 4 consecutive
 //     columns and, at step t, works on row t - l.  The only cross-lane value a row needs
 //     (Q[i-1][first column - 1]) was produced by the left neighbour two steps earlier, so
 //     its shuffle is issued one step ahead and its latency never sits on the chain.  What
 //     is left on the chain per step is FMNMX -> FADD; per cell the step costs FSET + FMNMX
 //     (ALU pipe) and FFMA + FADD (FMA pipe): the backpointer bit is accumulated as a float
-//     (FSET gives 1.0/0.0, an FFMA tree packs C of them into a mantissa).  A row step is
-//     issue-bound (measured: 37 cycles at C=4, 73 at C=8, tools/ubench/chain.cu), so C=4 is used
-//     while every strip warp still gets an SM sub-partition to itself, C=8 beyond that.
-//   * Strips of an utterance wider than one warp form a second, coarser wavefront: strip s runs
-//     >= 31 + 8 rows behind strip s-1 and takes one boundary value per row from a small
-//     shared-memory ring (release/acquire progress counters, both directions).
-//   * Each strip warp feeds itself: it owns a ring of logit rows in shared memory and, every
-//     8 steps, re-arms the stage its last lane has just left with ONE tiled TMA copy per
-//     128-column segment (cp.async.bulk.tensor.3d, box = 8 rows x pitch columns), completion
-//     on an mbarrier.  No producer warp, no "empty" barriers.  The box width is the smem row
-//     pitch; it comes from a small set (36/68/100/132 floats for C=8, 40/72/104/136 for C=4)
-//     chosen so that the skewed 16 B reads are bank-conflict-free and ragged utterances fetch
-//     little more than their valid T2_b columns.  Rows past T1_b are never requested.
-//   * Backpointers cost one bit per cell, in shared memory when the slot's bits fit, else in
-//     the caller's workspace (L2-resident).  C=8: one byte per lane and row, i.e. row-major bits
-//     (column j at bit j%32 of word j/32).  C=4: one byte per lane and ROW PAIR (low nibble =
-//     even row), unpacked by the backtrack when it fetches a window.
-//   * filler warp: zero-fills the utterance's dense int16 block and duration row with 16 B
-//     streaming stores while the DP runs.
-//   * backtrack (strip warp 0): 32 rows per block.  Every lane fetches the 32-column window
-//     its row can touch (the path moves at most one column per row); the windows are
-//     broadcast through shared memory and the dependent chain runs on a one-hot position
-//     register, two ALU levels per row:  R' = (R & ~A) | ((R >> 1) & (A >> 1)); each lane then
-//     picks its own row's position out of the 32 chain values with a 5-level select tree (a
-//     store per row inside the chain costs 3x more, tools/ubench/chain.cu).  Then all 32 lanes
-//     write their row's 1 and the durations of the tokens that start in the block (ballot +
-//     clz), so nothing is re-read to build durations.
+//     (FSET gives 1.0/0.0; an FFMA tree packs a row's 4 bits, one more FFMA files them under
+//     the step's nibble), so a lane emits one 32-bit word of bits per 8 steps.
+//   * Steps come in chunks of 16.  Everything that synchronises happens once per chunk: an
+//     mbarrier wait costs the warp >= 80 cycles even when the phase is long complete, an
+//     acquire load ~70, so neither may appear per step.
+//   * The logits reach a strip through a ring of 16-row stages in shared memory, filled by the
+//     strip's own loader warp (one lane) with tiled TMA copies (cp.async.bulk.tensor.3d, box =
+//     16 rows x the utterance's columns of the strip rounded up to 8; one op costs the issuing
+//     lane ~150 cycles whatever its size, hence >= 4 KB boxes and one loader per strip), "full"
+//     and "empty" mbarriers.  Because of the lane skew a stage stays live for 4 chunks; the
+//     rest of the ring is prefetch depth.  The row pitch is the box width, a multiple of 8
+//     floats, which makes the skewed 16 B reads bank-conflict-free.  Rows past T1_b and columns
+//     past T2_b (rounded up) are never requested.  Bases or strides that are not 16 B aligned
+//     take 4 B cp.async copies issued by the whole loader warp instead.
+//   * Strips of an utterance wider than 128 tokens form a second, coarser wavefront: strip s
+//     runs 3 chunks behind strip s-1 and takes its boundary values, 16 per chunk, from a small
+//     shared-memory ring; progress counters in both directions are plain shared words, read a
+//     chunk ahead of their use.
+//   * Backpointers cost one bit per cell: word (c, L) holds, for global lane L = column / 4,
+//     the nibbles of steps 8c .. 8c+7 (rows 8c - l + k).  In shared memory when the slot's
+//     bits fit next to a deep enough ring, else in the caller's workspace (coalesced 128 B
+//     stores, L2-resident).
+//   * The filler warp zero-fills the utterance's dense int16 block: bulk shared->global
+//     copies of a zero page (one lane), paced over the duration of the DP.
+//   * backtrack (strip warp 0): 32 rows per block.  Every lane assembles the 32-column window
+//     its row can touch (the path moves at most one column per row) from the skewed words;
+//     the windows are broadcast through shared memory and the dependent chain runs on a
+//     one-hot position register, two ALU levels per row:  R' = (R & ~A) | ((R >> 1) & (A >> 1)).
+//     Then all 32 lanes write their row's 1 and the durations of the tokens that start in
+//     the block (ballot + clz), so nothing is re-read to build durations.
 //
 // Bit-exactness: each cell does exactly the reference's one fp32 add on top of an exact
 // max; the comparison is the reference's `>=` (ties and -inf >= -inf take the diagonal).
@@ -62,16 +67,19 @@
 
 namespace isp {
 
-constexpr int kR = 8;                 // rows per ring stage (= steps per unrolled chunk = TMA box height)
+constexpr int kR = 16;                // steps per chunk = rows per ring stage = rows per TMA box
+constexpr int kC = 4;                 // columns per lane
+constexpr int kW = 32 * kC;           // columns per strip warp
 constexpr int kMaxStages = 16;
-constexpr int kMaxStrips = 8;         // ISP_MAS_MAX_T2 / 128
+constexpr int kMinStages = 5;         // 4 live + 1 in flight
+constexpr int kMaxStrips = 5;         // ISP_MAS_MAX_T2 / kW
 constexpr int kMaxSlots = 2;
-constexpr int kMaxThreads = 320;      // slots * (strips + 1) warps <= 10
-constexpr int kBnd = 256;             // rows in a strip-boundary ring (power of two, multiple of kR)
-constexpr int kMinRing = 48;          // 31 (lane skew) + kR (stage granularity) + kR (read-ahead), rounded up
-constexpr int kSlotHdr = 2048;        // barriers, counters, backtrack windows
-constexpr int kSeg = 128;             // columns per ring segment (one TMA box wide)
-constexpr int kNumBox = 4;            // box widths: base + 32 i floats, base = 36 (C = 8) or 40 (C = 4)
+constexpr int kMaxThreads = 352;      // slots * (2 * strips + 1) warps <= 11
+constexpr int kBnd = 128;             // rows in a strip-boundary ring
+constexpr int kBndChunks = kBnd / kR; // = 8, power of two
+constexpr int kZeroPage = 4096;       // bytes of zeros behind the bulk zero-fill
+constexpr int kSlotHdr = 2560;        // barriers (2 x 1 KB, 512 B used), progress counters (256 B), backtrack windows (256 B)
+constexpr int kNumBox = kW / 8;       // TMA box widths: 8, 16, ..., 128 columns
 
 struct MasParams {
     const float* logp;
@@ -87,62 +95,100 @@ struct MasParams {
     long long* probe;      // clock64 stamps of utterance 0 (tools/mas_probe.py)
     int ns;                // strip warps per utterance
     int slots;             // utterances per CTA
-    int full_floats;       // allocated ring-row floats of a full strip (all segments)
-    int last_floats[2];    // allocated pitch of segment 0 / 1 of the last strip
-    int ring_rows;         // rows per strip ring (multiple of kR)
-    int bits_pitch;        // bytes per row (C = 8) or row pair (C = 4) of bits, = ns * 32
+    int nstg;              // ring stages
+    int wlast;             // ring row floats allocated for the last strip (multiple of 8)
     int slot_bytes;        // shared memory per slot
-    int tma;               // 1: tensor maps are valid -> tiled TMA copies
+    int tma;               // 1: the tensor maps are valid -> tiled TMA copies, else 4 B async copies
     int dbg;               // debug/profiling switches (mas.dbg)
 };
 
 struct MasMaps { CUtensorMap m[kNumBox]; };
 
-// smallest box (index, width in floats) that covers `cols` (1..128) columns
-template <int C> __host__ __device__ inline int box_index(int cols) {
-    const int base = C == 8 ? 36 : 40;
-    return cols <= base ? 0 : (cols - base + 31) / 32;
-}
-template <int C> __host__ __device__ inline int box_width(int idx) { return (C == 8 ? 36 : 40) + 32 * idx; }
-
-// ---- zero-fill of [p, p+bytes) with 16 B streaming stores (any alignment) ------------
-ISP_DEVINL void warp_zero_fill(char* p, size_t bytes, int lane) {
-    size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
-    if (head > bytes) head = bytes;
-    for (size_t k = lane * 2; k < head; k += 64) *reinterpret_cast<int16_t*>(p + k) = 0;
-    char* body = p + head;
-    size_t nvec = (bytes - head) >> 4;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    size_t v = lane;
-    for (; v + 96 < nvec; v += 128) {
-        st_cs_v4(body + (v << 4), z);
-        st_cs_v4(body + ((v + 32) << 4), z);
-        st_cs_v4(body + ((v + 64) << 4), z);
-        st_cs_v4(body + ((v + 96) << 4), z);
-    }
-    for (; v < nvec; v += 32) st_cs_v4(body + (v << 4), z);
-    char* tail = body + (nvec << 4);
-    size_t tbytes = bytes - head - (nvec << 4);
-    for (size_t k = lane * 2; k < tbytes; k += 64) *reinterpret_cast<int16_t*>(tail + k) = 0;
-}
-
-ISP_DEVINL void tma_load_box(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
+// ---- small PTX helpers ---------------------------------------------------------------
+ISP_DEVINL void tma_load_box(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
         : "memory");
+}
+ISP_DEVINL int ld_volatile_sa(uint32_t saddr) {
+    int v;
+    asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+ISP_DEVINL void st_volatile_sa(uint32_t saddr, int v) {
+    asm volatile("st.volatile.shared::cta.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+ISP_DEVINL void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+ISP_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+ISP_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+ISP_DEVINL void cp_async4(uint32_t sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+ISP_DEVINL void cp_async_arrive_noinc_sa(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+ISP_DEVINL void mbar_arrive_sa(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+ISP_DEVINL void mbar_expect_tx_sa(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+ISP_DEVINL uint32_t mbar_test_sa(uint32_t bar, uint32_t parity) {     // non-blocking
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+ISP_DEVINL uint32_t mbar_try_sa(uint32_t bar, uint32_t parity) {      // may sleep in hardware
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// the loaders' wait: sleeps in hardware (up to ~1 us per try) instead of spinning on an issue port a strip warp needs
+ISP_DEVINL void mbar_wait_idle_sa(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000u) : "memory");
+        if (++spins > (1u << 24)) __trap();
+    } while (!ok);
+}
+// spin with a watchdog: a protocol bug must surface as a launch failure, not as a hung GPU
+ISP_DEVINL void mbar_wait_sa(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_sa(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
 }
 ISP_DEVINL float set_ge(float a, float b) {   // 1.0f if a >= b (false on NaN), else 0.0f: one FSET
     float d;
     asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
     return d;
 }
-template <int C> ISP_DEVINL void lds_row(float (&x)[C], uint32_t saddr) {
+ISP_DEVINL void lds_row(float (&x)[kC], uint32_t saddr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(saddr));
-    if (C == 8) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(x[4 % C]), "=f"(x[5 % C]), "=f"(x[6 % C]), "=f"(x[7 % C]) : "r"(saddr));
 }
-ISP_DEVINL void sts_u8(uint32_t saddr, uint32_t v) {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+ISP_DEVINL float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+ISP_DEVINL void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+ISP_DEVINL void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+ISP_DEVINL uint4 lds_v4(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+ISP_DEVINL void st_release_sa(uint32_t saddr, int v) {
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+ISP_DEVINL int ld_acquire_sa(uint32_t saddr) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
 }
 
 // one backtrack row on a one-hot position: stay where A is 0, move one column down where A is 1.
@@ -153,286 +199,337 @@ ISP_DEVINL uint32_t bt_step(uint32_t R, uint32_t A, uint32_t A1) {
     asm("lop3.b32 %0, %1, %2, %3, 0xf8;" : "=r"(out) : "r"(P), "r"(Rs), "r"(A1));   // P | (Rs & A1)
     return out;
 }
-// low nibbles of the 4 bytes of w (after >> shift) packed into 16 bits
-ISP_DEVINL uint32_t pack_nibbles(uint32_t w, int shift) {
-    uint32_t x = (w >> shift) & 0x0f0f0f0fu;
-    x = (x | (x >> 4)) & 0x00ff00ffu;
-    return (x | (x >> 8)) & 0xffffu;
-}
 
 // ---- one DP row for one lane --------------------------------------------------------
-// q[] holds row i-1 on entry and row i on exit.  Returns the lane's C backpointer bits in
-// the low bits (bit c set <=> predecessor of column base+c is the diagonal).
-template <int C> ISP_DEVINL uint32_t dp_row(float (&q)[C], const float (&x)[C], float left) {
-    float s[C];
+// q[] holds row i-1 on entry and row i on exit.  Returns the lane's 4 backpointer bits as a
+// float 0..15 (bit c set <=> the predecessor of column base+c is the diagonal).
+ISP_DEVINL float dp_row(float (&q)[kC], const float (&x)[kC], float left) {
+    float s[kC];
 #pragma unroll
-    for (int c = C - 1; c >= 1; --c) {
+    for (int c = kC - 1; c >= 1; --c) {
         s[c] = set_ge(q[c - 1], q[c]);                // mas.py:17 -- ties take j-1
         q[c] = x[c] + fmaxf(q[c - 1], q[c]);          // mas.py:14 -- one fp32 add per cell
     }
     s[0] = set_ge(left, q[0]);                        // left == NaN at global column 0: false, keeps q[0]
     q[0] = x[0] + fmaxf(left, q[0]);
-    const float t0 = fmaf(s[1], 2.0f, s[0]), t1 = fmaf(s[3], 2.0f, s[2]);
-    float v = fmaf(t1, 4.0f, t0);
-    if (C == 8) {
-        const float t2 = fmaf(s[5 % C], 2.0f, s[4 % C]), t3 = fmaf(s[7 % C], 2.0f, s[6 % C]);
-        v = fmaf(fmaf(t3, 4.0f, t2), 16.0f, v);
-    }
-    return __float_as_uint(v + 8388608.0f);           // integer 0..2^C-1 in the low mantissa bits
+    return fmaf(fmaf(s[3], 2.0f, s[2]), 4.0f, fmaf(s[1], 2.0f, s[0]));
 }
 
-template <int C, bool BITS_SMEM, bool MULTI>
+template <bool BITS_SMEM> ISP_DEVINL uint4 load_bits4(const uint32_t* gp, uint32_t sa) {
+    if (BITS_SMEM) return lds_v4(sa);
+    return __ldcg(reinterpret_cast<const uint4*>(gp));
+}
+
+template <bool BITS_SMEM, bool MULTI>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
-    constexpr int W = 32 * C;            // columns per strip
-    constexpr int NSEG = W / kSeg;       // ring segments per strip (1 or 2)
-    constexpr int LPS = kSeg / C;        // lanes per segment
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
+    // warps of a CTA: [slots x ns strips][slots x ns loaders][slots fillers]
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ns = p.ns;
     const int nstrip_total = p.slots * ns;
-    const bool is_strip = warp < nstrip_total;
-    const int slot = is_strip ? warp / ns : warp - nstrip_total;
-    const int s = is_strip ? warp - slot * ns : 0;
+    const int role = warp < nstrip_total ? 0 : (warp < 2 * nstrip_total ? 1 : 2);    // strip, loader, filler
+    const int wrel = warp - role * nstrip_total;
+    const int slot = role == 2 ? wrel : wrel / ns;
+    const int s = role == 2 ? 0 : wrel - slot * ns;
+    const bool is_strip = role == 0;
     const int b = blockIdx.x * p.slots + slot;
     if (b >= p.B) return;                               // the whole slot leaves together
-    const uint32_t slot_threads = 32u * (ns + 1);
+    const uint32_t slot_threads = 32u * (2 * ns + 1);
+    const int nstg = p.nstg;
 
     // ---- carve the slot's shared memory -------------------------------------------------
     unsigned char* sm = smem_raw + size_t(slot) * p.slot_bytes;
-    uint64_t* full_all = reinterpret_cast<uint64_t*>(sm);                       // [kMaxStrips][kMaxStages]
-    int* prog = reinterpret_cast<int*>(sm + 1024);                              // [kMaxStrips] rows finished by lane 31
-    int* cons = prog + kMaxStrips;                                              // [kMaxStrips] rows entered by lane 0
-    uint32_t* winbuf = reinterpret_cast<uint32_t*>(sm + 1024 + 64);             // [32][2] backtrack windows (A, A >> 1)
-    float* bnd = reinterpret_cast<float*>(sm + kSlotHdr);                       // [ns-1][kBnd]
-    size_t off = kSlotHdr + (MULTI ? sizeof(float) * size_t(ns - 1) * kBnd : 0);
-    float* ring_all = reinterpret_cast<float*>(sm + off);
-    const int last_total = p.last_floats[0] + p.last_floats[1];
-    off += sizeof(float) * (size_t(p.ring_rows) * (size_t(ns - 1) * p.full_floats + last_total) + kSeg);  // + kSeg: lanes past the last valid column read on
-    unsigned char* bits_base;
-    if (BITS_SMEM) bits_base = sm + off;
-    else bits_base = reinterpret_cast<unsigned char*>(p.bits_ws + size_t(b) * p.bits_stride);
+    const uint32_t sm_sa = smem_u32(sm);
+    const uint32_t full_sa = sm_sa;                                             // [kMaxStrips][kMaxStages] u64: stage has landed
+    const uint32_t empty_sa = sm_sa + 1024;                                     // [kMaxStrips][kMaxStages] u64: stage may be refilled
+    const uint32_t prog_sa = sm_sa + 2048;                                      // [kMaxStrips] chunks whose last column strip s has published
+    const uint32_t cons_sa = prog_sa + 4 * kMaxStrips;                          // [kMaxStrips] chunks whose boundary values strip s has taken
+    uint32_t* winbuf = reinterpret_cast<uint32_t*>(sm + 2304);                  // [32][2] backtrack windows (A, A >> 1)
+    uint32_t off = kSlotHdr;
+    const uint32_t bnd_sa = sm_sa + off;                                        // [ns-1][kBnd] floats
+    off += MULTI ? 4u * uint32_t(ns - 1) * kBnd : 0u;
+    const uint32_t zero_sa = sm_sa + off;
+    off += kZeroPage;
+    const uint32_t ring_sa = sm_sa + off;                                       // strip s: ring_sa + s * nstg * kR * kW * 4
+    off += uint32_t(nstg) * kR * uint32_t((ns - 1) * kW + p.wlast) * 4u;
+    const int wpt = ns * 32;                                                    // words of bits per 8 steps
+    const uint32_t bits_sa = sm_sa + off;
+    uint32_t* bits_g = BITS_SMEM ? nullptr : p.bits_ws + size_t(b) * p.bits_stride;
 
     // ---- lengths (read on device; clamped for memory safety, reported via status) ------
     const long long n64 = p.mel_len[b], m64 = p.text_len[b];
     const bool bad = n64 < 1 || n64 > p.T1max || m64 < 1 || m64 > p.T2max;
     const int n = int(n64 < 1 ? 1 : (n64 > p.T1max ? p.T1max : n64));   // frames
     const int m = int(m64 < 1 ? 1 : (m64 > p.T2max ? p.T2max : m64));   // tokens
-    const int ns_active = (m + W - 1) / W;
-    const int nstg = p.ring_rows / kR;
-    const bool probe_w = p.probe != nullptr && b == 0 && is_strip && s == 0;   // warp-uniform
-    const bool probe = probe_w && lane == 0;
-    long long pc_issue = 0, pc_wait = 0;
+    const int ns_active = (m + kW - 1) / kW;
+    const int nch = (n + 31 + kR - 1) / kR;                             // chunks of a strip's n + 31 steps
+    const bool probe_w = p.probe != nullptr && b == 0 && s == 0;        // warp-uniform
+    const bool probe = probe_w && is_strip && lane == 0;
+    long long pc_full = 0, pc_flag = 0;
 
-    if (is_strip && lane == 0) {
-        if (s == 0 && bad) atomicAdd(p.status, 1);
-        for (int st = 0; st < nstg; ++st) mbar_init(&full_all[s * kMaxStages + st], 1);
-        prog[s] = 0;
-        cons[s] = 0;
-        fence_mbar_init();
+    // per strip: the utterance's columns, the TMA box / ring row width and the ring
+    const int mcols = max(0, min(kW, m - s * kW));
+    const int wb = (mcols + 7) & ~7;                                    // floats per ring row
+    const uint32_t pitchB = uint32_t(wb) * 4u;
+    const uint32_t stageB = uint32_t(kR) * pitchB;
+    const uint32_t ringB = uint32_t(nstg) * stageB;
+    const uint32_t ring_s = ring_sa + uint32_t(s) * uint32_t(nstg) * kR * kW * 4u;
+    const uint32_t full_s = full_sa + uint32_t(s) * kMaxStages * 8u;
+    const uint32_t empty_s = empty_sa + uint32_t(s) * kMaxStages * 8u;
+
+    if (role == 0) {
+        if (lane == 0) {
+            if (s == 0 && bad) atomicAdd(p.status, 1);
+            for (int st = 0; st < nstg; ++st) {
+                mbar_init(reinterpret_cast<uint64_t*>(sm) + s * kMaxStages + st, p.tma ? 1 : 32);
+                mbar_init(reinterpret_cast<uint64_t*>(sm + 1024) + s * kMaxStages + st, 1);
+            }
+            reinterpret_cast<int*>(sm + 2048)[s] = 0;
+            reinterpret_cast<int*>(sm + 2048)[kMaxStrips + s] = 0;
+            fence_mbar_init();
+        }
+    } else if (role == 2) {
+        for (int i = lane; i < kZeroPage / 16; i += 32) reinterpret_cast<uint4*>(sm + (zero_sa - sm_sa))[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();                            // the zero page is read by bulk copies (async proxy)
     }
     asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(slot_threads) : "memory");
     if (probe) p.probe[0] = clock64();
 
-    if (is_strip) {
+    if (role == 0) {
         if (s < ns_active) {
             // =========================== strip warp: forward DP ===========================
-            const int mcols = min(W, m - s * W);                         // valid columns of this strip
-            // the strip's ring is NSEG segments of <= 128 columns, each filled by its own TMA box
-            const int cols0 = min(kSeg, mcols), cols1 = mcols - cols0;
-            const int bi0 = box_index<C>(cols0), bi1 = box_index<C>(max(cols1, 1));
-            const int P0 = box_width<C>(bi0), P1 = (NSEG > 1 && cols1 > 0) ? box_width<C>(bi1) : 0;   // row pitch (floats)
-            float* ring0 = ring_all + size_t(s) * p.ring_rows * p.full_floats;
-            float* ring1 = ring0 + size_t(p.ring_rows) * (s == ns - 1 ? p.last_floats[0] : p.full_floats / NSEG);
-            uint64_t* full = full_all + s * kMaxStages;
-            const int nchunks = (n + kR - 1) / kR;
-            const uint64_t pol = policy_evict_first();
+            const uint32_t lane_ring = ring_s + min(uint32_t(lane) * 16u, pitchB - 16u);   // lanes past the box read (and discard) its last columns
             const bool has_prev = MULTI && s > 0;
             const bool has_next = MULTI && s + 1 < ns_active;
-            float* bnd_mine = bnd + size_t(s) * kBnd;
-            const float* bnd_prev = bnd + size_t(s > 0 ? s - 1 : 0) * kBnd;
-            const uint32_t chunk_tx = uint32_t(kR) * uint32_t(P0 + P1) * 4u;         // a box always lands whole
-
-            // (re)fill the next ring stage with rows [c*kR, c*kR + kR) -- warp-collective; chunks are issued in
-            // order, so the stage index just cycles (no runtime division on the chain)
-            int issue_st = 0;
-            auto issue_chunk = [&](int c) {
-                const int st = issue_st;
-                issue_st = issue_st + 1 == nstg ? 0 : issue_st + 1;
-                const int r0 = c * kR;
-                __syncwarp();                          // every lane is done reading this stage
-                if (p.tma) {
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&full[st], chunk_tx);
-                        tma_load_box(ring0 + size_t(st) * kR * P0, &maps.m[bi0], s * W, r0, b, &full[st], pol);
-                        if (NSEG > 1 && cols1 > 0) tma_load_box(ring1 + size_t(st) * kR * P1, &maps.m[bi1], s * W + kSeg, r0, b, &full[st], pol);
-                    }
-                } else {
-                    // tensor maps unavailable (unaligned base or strides): coalesced 4 B loads through registers
-                    const int rows = min(kR, n - r0);
-                    const float* src = p.logp + int64_t(b) * p.sB + s * W + int64_t(r0) * p.sT1;
-                    for (int r = 0; r < rows; ++r) {
-                        const float* g = src + int64_t(r) * p.sT1;
-                        for (int c2 = lane; c2 < cols0; c2 += 32) ring0[(size_t(st) * kR + r) * P0 + c2] = __ldg(g + c2);
-                        if (NSEG > 1) for (int c2 = lane; c2 < cols1; c2 += 32) ring1[(size_t(st) * kR + r) * P1 + c2] = __ldg(g + kSeg + c2);
-                    }
-                    __syncwarp();
-                }
-            };
-            int wait_st = 0;
-            uint32_t wait_ph = 0;
-            auto wait_chunk = [&]() {                  // chunks are waited for in order
-                if (p.tma) mbar_wait(&full[wait_st], wait_ph);
-                if (++wait_st == nstg) { wait_st = 0; wait_ph ^= 1u; }
-            };
-
-            for (int c = 0; c < nstg && c < nchunks; ++c) issue_chunk(c);
-
-            // lanes [0, LPS) read segment 0, the rest segment 1 (a lane past the valid columns reads stale rows)
-            const bool in1 = NSEG > 1 && lane >= LPS && cols1 > 0;
-            const uint32_t ring_sa = smem_u32(in1 ? ring1 : ring0);
-            const uint32_t pitchB = uint32_t(in1 ? P1 : P0) * 4u;
-            const uint32_t ringB = uint32_t(p.ring_rows) * pitchB;
-            // byte offset of this lane's columns in the ring row it reads next (row t+1-lane, one step ahead)
-            uint32_t xoff = uint32_t((p.ring_rows - lane) % p.ring_rows) * pitchB + uint32_t(lane % LPS) * (C * 4);
+            const bool pub = has_next && lane == 31;                // this lane publishes the strip's last column
+            // boundary rings: row r of strip s's last column lives in slot (r + 31) mod kBnd of ring s, i.e. at the
+            // producer's step index -- chunk-aligned for the writer; the reader's 16 rows straddle two chunks (15 | 0..14)
+            const uint32_t bnd_mine = bnd_sa + uint32_t(s) * kBnd * 4u;
+            const uint32_t bnd_prev = bnd_sa + uint32_t(s > 0 ? s - 1 : 0) * kBnd * 4u;
             const float qnan = __int_as_float(0x7fffffff);
-            float q[C], xc[C];
+            const int gcol0 = s * kW + lane * kC;
+
+            float q[kC], xc[kC];
 #pragma unroll
-            for (int c = 0; c < C; ++c) q[c] = -CUDART_INF_F;
+            for (int c = 0; c < kC; ++c) q[c] = -CUDART_INF_F;
             float left_cur = qnan;
-            const int gcol0 = s * W + lane * C;
-            const uint32_t bpB = uint32_t(p.bits_pitch);
-            // C = 8: this lane's bits byte for row (t0 - lane) + k is at bits_* + k * bpB;
-            // C = 4: for row pair ((t0 - lane) >> 1) + (k >> 1), written on the pair's odd row.  Advanced once per chunk.
-            uint32_t bits_sa = 0;
-            unsigned char* bits_g = nullptr;
-            {
-                const int64_t first = C == 8 ? -int64_t(lane) : -int64_t((lane + 1) >> 1);     // (0 - lane) >> 1, arithmetic
-                if (BITS_SMEM) bits_sa = smem_u32(bits_base) + uint32_t(s * 32 + lane) + uint32_t(int32_t(first)) * bpB;
-                else bits_g = bits_base + (s * 32 + lane) + first * int64_t(bpB);
-            }
-            uint32_t nib_lo = 0;                           // C = 4: the even row's nibble, waiting for its odd row
-            const bool lane_odd = (lane & 1) != 0;
 
-            wait_chunk();
-            lds_row<C>(xc, ring_sa + xoff);
-            xoff += pitchB; if (xoff >= ringB) xoff -= ringB;
+            // ring row (byte offset inside the ring) this lane reads next: row (t + 1 - lane) mod ring at step t
+            uint32_t rd = (uint32_t(nstg * kR) - uint32_t(lane)) * pitchB;
+            if (rd >= ringB) rd -= ringB;
+            mbar_wait_sa(full_s, 0);                                   // chunk 0
+            lds_row(xc, lane_ring + rd);                               // the row of step 0
+            rd += pitchB; if (rd >= ringB) rd -= ringB;
+            int st_wait = 1;                                           // stage of chunk ch + 1
+            uint32_t ph_wait = 0u;
+            int st_free = 0;                                           // stage of chunk ch - 3
+            int st_cur = 0;                                            // stage of chunk ch
+            uint32_t bits_off = uint32_t(s * 32 + lane) * 4u;          // byte offset of this lane's first word of chunk ch
+            int prog_seen = 0, cons_seen = 0, p_early = 0, c_early = 0;
 
-            const int nsteps = n + 31;
-            for (int t0 = 0; t0 < nsteps; t0 += kR) {
-                const int ch = t0 / kR;
-                long long c0 = 0, c1 = 0, c2 = 0;
-                if (probe_w) c0 = clock64();
-                {   // the stage lane 31 left during the previous chunk is free: re-arm it
-                    const int f = (t0 - 31 >= 0 ? (t0 - 31) / kR : -1) - 1;
-                    if (f >= 0 && f + nstg < nchunks) issue_chunk(f + nstg);
+            for (int ch = 0; ch < nch; ++ch) {
+                const int t0 = ch * kR;
+                // ---- chunk top: free the stage whose last reader has moved on ----
+                if (ch >= 3) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_sa(empty_s + uint32_t(st_free) * 8u);
+                    st_free = st_free + 1 == nstg ? 0 : st_free + 1;
                 }
-                if (probe_w) c1 = clock64();
-                if (ch + 1 < nchunks) wait_chunk();      // the read-ahead of this chunk's last step lands there
-                if (probe_w) { c2 = clock64(); pc_issue += c1 - c0; pc_wait += c2 - c1; }
+                const bool wait_next = ch + 1 < nch;                   // lane 0's read-ahead crosses into the next stage on the last step
+                float bvals[kR];
+#pragma unroll
+                for (int k = 0; k < kR; ++k) bvals[k] = qnan;
+                uint32_t pub_sa = 0;
                 if (MULTI) {
-                    if (lane == 0) {
-                        uint32_t spins = 0;
-                        if (has_prev) {
-                            st_release_shared(&cons[s], t0);
-                            const int need = min(t0 + kR, n);          // boundary rows this chunk consumes
-                            while (ld_acquire_shared(&prog[s - 1]) < need) { if (++spins > (1u << 26)) __trap(); }
+                    if (has_prev) {
+                        // the boundary values of rows t0 .. t0+15: the producer must have published its chunks <= ch + 2
+                        const int need = min(ch + 3, nch);
+                        prog_seen = max(prog_seen, p_early);
+                        if (prog_seen < need) {
+                            long long c0 = 0;
+                            if (probe_w) c0 = clock64();
+                            uint32_t spins = 0;
+                            do {
+                                prog_seen = ld_acquire_sa(prog_sa + 4u * (s - 1));
+                                if (++spins > (1u << 26)) __trap();
+                            } while (prog_seen < need);
+                            if (probe_w) pc_flag += clock64() - c0;
                         }
-                        if (has_next) {
-                            const int need = t0 - 31 + kR - kBnd + 1;  // do not lap the reader of our boundary ring
-                            while (ld_acquire_shared(&cons[s + 1]) < need) { if (++spins > (1u << 26)) __trap(); }
-                        }
+                        const uint32_t b0 = bnd_prev + uint32_t(((ch + 1) & (kBndChunks - 1)) * kR) * 4u;
+                        const uint32_t b1 = bnd_prev + uint32_t(((ch + 2) & (kBndChunks - 1)) * kR) * 4u;
+                        bvals[0] = lds_f32(b0 + 60u);
+                        const uint4 u0 = lds_v4(b1), u1 = lds_v4(b1 + 16u), u2 = lds_v4(b1 + 32u), u3 = lds_v4(b1 + 48u);
+                        bvals[1] = __uint_as_float(u0.x); bvals[2] = __uint_as_float(u0.y); bvals[3] = __uint_as_float(u0.z); bvals[4] = __uint_as_float(u0.w);
+                        bvals[5] = __uint_as_float(u1.x); bvals[6] = __uint_as_float(u1.y); bvals[7] = __uint_as_float(u1.z); bvals[8] = __uint_as_float(u1.w);
+                        bvals[9] = __uint_as_float(u2.x); bvals[10] = __uint_as_float(u2.y); bvals[11] = __uint_as_float(u2.z); bvals[12] = __uint_as_float(u2.w);
+                        bvals[13] = __uint_as_float(u3.x); bvals[14] = __uint_as_float(u3.y); bvals[15] = __uint_as_float(u3.z);
+                        p_early = ld_volatile_sa(prog_sa + 4u * (s - 1));   // looked at one chunk from now
+                        if (lane == 0) st_volatile_sa(cons_sa + 4u * s, ch); // the values of chunks < ch are in registers
                     }
-                    __syncwarp();
+                    if (has_next) {
+                        // this chunk overwrites the slots written 8 chunks ago, which the reader takes in its chunks <= ch - 9
+                        const int need = ch - 8;
+                        cons_seen = max(cons_seen, c_early);
+                        if (cons_seen < need) {
+                            long long c0 = 0;
+                            if (probe_w) c0 = clock64();
+                            uint32_t spins = 0;
+                            do {
+                                cons_seen = ld_acquire_sa(cons_sa + 4u * (s + 1));
+                                if (++spins > (1u << 26)) __trap();
+                            } while (cons_seen < need);
+                            if (probe_w) pc_flag += clock64() - c0;
+                        }
+                        c_early = ld_volatile_sa(cons_sa + 4u * (s + 1));
+                        pub_sa = bnd_mine + uint32_t((ch & (kBndChunks - 1)) * kR) * 4u;
+                    }
                 }
-                if (t0 >= 32 && t0 + kR <= n) {
-                    // ---- steady state: every lane has a valid row >= 1 for all kR steps ----
-#pragma unroll
-                    for (int k = 0; k < kR; ++k) {
-                        const float nxt = __shfl_up_sync(0xffffffffu, q[C - 1], 1);
-                        float xn[C];
-                        lds_row<C>(xn, ring_sa + xoff);
-                        xoff += pitchB; if (xoff >= ringB) xoff -= ringB;
-                        float bv = qnan;
-                        if (has_prev) bv = bnd_prev[(t0 + k) & (kBnd - 1)];
-                        const uint32_t bits = dp_row<C>(q, xc, left_cur);
-                        if (C == 8) {
-                            if (BITS_SMEM) sts_u8(bits_sa + uint32_t(k) * bpB, bits);
-                            else bits_g[int64_t(k) * bpB] = static_cast<unsigned char>(bits);
-                        } else {
-                            // row parity of this lane at step k is (k + lane) & 1 (t0 is a multiple of 8)
-                            const uint32_t byte = nib_lo | (bits << 4);
-                            if (((k & 1) != 0) != lane_odd) {
-                                if (BITS_SMEM) sts_u8(bits_sa + uint32_t(k >> 1) * bpB, byte);
-                                else bits_g[int64_t(k >> 1) * bpB] = static_cast<unsigned char>(byte);
-                            }
-                            nib_lo = bits & 15u;
-                        }
-                        if (has_next && lane == 31) bnd_mine[(t0 + k - 31) & (kBnd - 1)] = q[C - 1];
-                        left_cur = lane == 0 ? bv : nxt;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) xc[c] = xn[c];
+                uint32_t word0, word1;
+                const bool steady = t0 >= 32 && t0 + kR <= n;
+                // one step; WRAP: the ring may wrap inside the chunk for some lanes; EDGE: some lanes are before row 0 or past row n-1
+#define ISP_MAS_STEP(WRAP, EDGE)                                                                                   \
+                    {                                                                                              \
+                        if (k == 8 && wait_next) {                                                                 \
+                            long long c0 = 0;                                                                      \
+                            if (probe_w) c0 = clock64();                                                           \
+                            mbar_wait_sa(full_s + uint32_t(st_wait) * 8u, ph_wait);                                \
+                            if (probe_w) pc_full += clock64() - c0;                                                \
+                        }                                                                                          \
+                        const float nxt = __shfl_up_sync(0xffffffffu, q[kC - 1], 1);                               \
+                        float xn[kC];                                                                              \
+                        lds_row(xn, lane_ring + rd);                                                               \
+                        rd += pitchB;                                                                              \
+                        if (WRAP) { if (rd >= ringB) rd -= ringB; }                                                \
+                        const float v = dp_row(q, xc, left_cur);                                                   \
+                        if (EDGE) {                                                                                \
+                            if (t0 + k - lane == 0) {                                                              \
+                                /* row 0: Q[0][0] = x[0][0], Q[0][j>0] = -inf   (mas.py:11) */                     \
+                                _Pragma("unroll") for (int c = 0; c < kC; ++c) q[c] = (gcol0 + c == 0) ? xc[c] : -CUDART_INF_F; \
+                            }                                                                                      \
+                        }                                                                                          \
+                        acc[k >> 2] = fmaf(v, float(1 << (4 * (k & 3))), acc[k >> 2]);                             \
+                        if (MULTI && pub) sts_f32(pub_sa + uint32_t(k) * 4u, q[kC - 1]);   /* rows outside [0, n) are never consumed */ \
+                        left_cur = lane == 0 ? bvals[k] : nxt;                                                     \
+                        _Pragma("unroll") for (int c = 0; c < kC; ++c) xc[c] = xn[c];                              \
                     }
+                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (steady && st_cur >= 2 && st_cur + 1 < nstg) {
+                    // the lanes read rows t0 - 30 .. t0 + 16, i.e. stages st_cur - 2 .. st_cur + 1: no wrap
+#pragma unroll
+                    for (int k = 0; k < kR; ++k) ISP_MAS_STEP(false, false)
+                } else if (steady) {
+#pragma unroll
+                    for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, false)
                 } else {
-                    // ---- head and tail: some lanes are before row 0 or past row n-1 ----
-                    for (int k = 0; k < kR; ++k) {
-                        const int t = t0 + k;
-                        const int r = t - lane;
-                        const float nxt = __shfl_up_sync(0xffffffffu, q[C - 1], 1);
-                        float xn[C];
-                        lds_row<C>(xn, ring_sa + xoff);
-                        xoff += pitchB; if (xoff >= ringB) xoff -= ringB;
-                        float bv = qnan;
-                        if (has_prev) bv = bnd_prev[t & (kBnd - 1)];
-                        const uint32_t bits = dp_row<C>(q, xc, left_cur);
-                        if (r == 0) {
-                            // row 0: Q[0][0] = x[0][0], Q[0][j>0] = -inf   (mas.py:11)
 #pragma unroll
-                            for (int c = 0; c < C; ++c) q[c] = (gcol0 + c == 0) ? xc[c] : -CUDART_INF_F;
-                        }
-                        if (C == 8) {
-                            if (r >= 1 && r < n) {
-                                if (BITS_SMEM) sts_u8(bits_sa + uint32_t(k) * bpB, bits);
-                                else bits_g[int64_t(k) * bpB] = static_cast<unsigned char>(bits);
-                            }
-                        } else if (r >= 0 && r < n) {
-                            // odd row: the pair is complete; even last row: flush the half pair
-                            const uint32_t byte = (r & 1) ? (nib_lo | (bits << 4)) : (bits & 15u);
-                            if ((r & 1) || r == n - 1) {
-                                const int po = (k + (lane & 1)) >> 1;          // pair of row r, relative to the chunk's base pair
-                                if (BITS_SMEM) sts_u8(bits_sa + uint32_t(po) * bpB, byte);
-                                else bits_g[int64_t(po) * bpB] = static_cast<unsigned char>(byte);
-                            }
-                            nib_lo = bits & 15u;
-                        }
-                        if (has_next && lane == 31 && r >= 0 && r < n) bnd_mine[r & (kBnd - 1)] = q[C - 1];
-                        left_cur = lane == 0 ? bv : nxt;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) xc[c] = xn[c];
-                    }
+                    for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, true)
                 }
-                if (BITS_SMEM) bits_sa += (C == 8 ? kR : kR / 2) * bpB; else bits_g += int64_t(C == 8 ? kR : kR / 2) * bpB;
-                if (has_next) {
-                    const int done = min(t0 + kR - 31, n);             // rows lane 31 has finished
-                    __syncwarp();
-                    if (done > 0 && lane == 31) st_release_shared(&prog[s], done);
+#undef ISP_MAS_STEP
+                if (rd >= ringB) rd -= ringB;                          // the no-wrap chunk may end exactly on the ring's end
+                word0 = __byte_perm(__float_as_uint(acc[0] + 8388608.0f), __float_as_uint(acc[1] + 8388608.0f), 0x5410);
+                word1 = __byte_perm(__float_as_uint(acc[2] + 8388608.0f), __float_as_uint(acc[3] + 8388608.0f), 0x5410);
+                if (BITS_SMEM) {
+                    sts_u32(bits_sa + bits_off, word0);
+                    sts_u32(bits_sa + bits_off + uint32_t(wpt) * 4u, word1);
+                } else {
+                    bits_g[bits_off >> 2] = word0;
+                    bits_g[(bits_off >> 2) + wpt] = word1;
                 }
+                bits_off += uint32_t(wpt) * 8u;
+                st_cur = st_cur + 1 == nstg ? 0 : st_cur + 1;
+                if (wait_next) { if (++st_wait == nstg) { st_wait = 0; ph_wait ^= 1u; } }
+                if (MULTI && pub) st_release_sa(prog_sa + 4u * s, ch + 1);   // releases this lane's 16 stores
             }
         }
+    } else if (role == 1) {
+        // =========================== loader warp of strip s ================================
+        if (s < ns_active) {
+            const bool lprobe = probe_w && lane == 0;
+            long long lp_wait = 0, lp_t0 = 0;
+            if (lprobe) lp_t0 = clock64();
+            const uint64_t pol = policy_evict_first();
+            const CUtensorMap* map = &maps.m[wb / 8 - 1];
+            const float* src_b = p.logp + int64_t(b) * p.sB + s * kW;
+            int st = 0;
+            uint32_t ph = 1u;                                         // parity to wait for on empty[st]: phase (c / nstg - 1)
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t full_b = full_s + uint32_t(st) * 8u;
+                if (c >= nstg) {
+                    long long c0 = 0;
+                    if (lprobe) c0 = clock64();
+                    if (p.tma) { if (lane == 0) mbar_wait_idle_sa(empty_s + uint32_t(st) * 8u, ph); }
+                    else mbar_wait_idle_sa(empty_s + uint32_t(st) * 8u, ph);
+                    if (lprobe) lp_wait += clock64() - c0;
+                }
+                const int r0 = kR * c;
+                const uint32_t dst = ring_s + uint32_t(st) * stageB;
+                if (p.tma) {
+                    if (lane == 0) {
+                        if (r0 < n && !(p.dbg & 8)) {
+                            mbar_expect_tx_sa(full_b, stageB);
+                            tma_load_box(dst, map, s * kW, r0, b, full_b, pol);
+                        } else {
+                            mbar_arrive_sa(full_b);                   // nothing to fetch: the strip's tail runs on stale rows
+                        }
+                    }
+                } else {
+                    // unaligned base or strides: 4 B async copies, one column per lane and pass
+                    if (r0 < n && !(p.dbg & 8)) {
+                        const int rows = min(kR, n - r0);
+                        for (int r = 0; r < rows; ++r)
+                            for (int col = lane; col < mcols; col += 32)
+                                cp_async4(dst + uint32_t(r) * pitchB + uint32_t(col) * 4u, src_b + int64_t(r0 + r) * p.sT1 + col);
+                    }
+                    cp_async_arrive_noinc_sa(full_b);
+                }
+                if (++st == nstg) { st = 0; ph ^= 1u; }
+            }
+            if (lprobe) { p.probe[6] = lp_wait; p.probe[7] = clock64() - lp_t0; }
+        }
+        __syncwarp();
     } else {
-        // =========================== filler warp: zero the outputs =====================
+        // =========================== filler warp: zero the outputs =========================
         const size_t cells = size_t(p.T1max) * p.T2max;
-        if (!(p.dbg & 4)) warp_zero_fill(reinterpret_cast<char*>(p.hard + size_t(b) * cells), cells * sizeof(int16_t), lane);
+        char* zbeg = reinterpret_cast<char*>(p.hard + size_t(b) * cells);
+        char* zend = zbeg + cells * sizeof(int16_t);
+        char* zb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(zbeg) + 15) & ~uintptr_t(15));
+        char* ze = reinterpret_cast<char*>(reinterpret_cast<uintptr_t>(zend) & ~uintptr_t(15));
+        if (ze < zb) ze = zb;
+        if (!(p.dbg & 4)) {
+            // unaligned head / tail of the dense block (at most 7 int16 each)
+            for (char* q2 = zbeg + 2 * lane; q2 < zb && q2 < zend; q2 += 64) *reinterpret_cast<int16_t*>(q2) = 0;
+            for (char* q2 = ze + 2 * lane; q2 < zend; q2 += 64) *reinterpret_cast<int16_t*>(q2) = 0;
+        } else {
+            ze = zb;
+        }
         if (p.dur) {
             int64_t* d = p.dur + size_t(b) * p.T2max;
             for (int j = lane; j < p.T2max; j += 32) d[j] = 0;
         }
+        if (lane == 0) {
+            // spread the copies over ~80 % of the forward pass (~20 ns per row) so that they do not crowd out the first loads
+            const long long pieces = (long long)((size_t(ze - zb) + kZeroPage - 1) / kZeroPage);
+            long long gap = pieces > 0 ? (16LL * n - 65LL * pieces) / pieces : 0;
+            if (gap < 0 || (p.dbg & 16)) gap = 0;
+            if (gap > 2000) gap = 2000;
+            for (char* zp = zb; zp < ze;) {
+                const uint32_t bytes = uint32_t(min(size_t(kZeroPage), size_t(ze - zp)));
+                bulk_s2g(zp, zero_sa, bytes);
+                bulk_commit();
+                zp += bytes;
+                if (gap > 0) __nanosleep(unsigned(gap));
+            }
+            bulk_wait_all();                              // the zeros are in place before the backtrack writes its ones
+            fence_proxy_async();
+        }
+        __syncwarp();
     }
 
     // bits (shared or global) and the zero-filled outputs become visible to the slot's warp 0
-    if (probe) { p.probe[1] = clock64(); p.probe[4] = pc_issue; p.probe[5] = pc_wait; }
+    if (probe) { p.probe[1] = clock64(); p.probe[4] = pc_full; p.probe[5] = pc_flag; }
     if (!BITS_SMEM) __threadfence_block();
     asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(slot_threads) : "memory");
     if (!is_strip || s != 0) return;
@@ -442,14 +539,28 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     // mas.py:20-24.  Rows i0, i0-1, ..., i0-31 per block; lane t owns row i0-t.
     int16_t* hard_b = p.hard + size_t(b) * p.T1max * p.T2max;
     int64_t* dur_b = p.dur ? p.dur + size_t(b) * p.T2max : nullptr;
-    const uint32_t* bits_w = reinterpret_cast<const uint32_t*>(bits_base);
-    const int wpr = p.bits_pitch >> 2;      // words per row (C = 8) / row pair (C = 4) of bits
-    // the 32 backpointer bits of columns [32 q, 32 q + 32) of row `row`
+    // The 32 backpointer bits of columns [32 qq, 32 qq + 32) of row `row`: global lane L = 8 qq + i holds row `row` in
+    // the word of chunk (row + l) >> 3 (l = L mod 32) at nibble (row + l) & 7  ->  for i = 0..7 the nibble index runs
+    // cyclically from a = row & 7 and the chunk steps once, where a + i reaches 8.
     auto bits_word = [&](int row, int qq) -> uint32_t {
-        if (C == 8) return bits_w[size_t(row) * wpr + qq];
-        const uint2 v = *reinterpret_cast<const uint2*>(bits_w + size_t(row >> 1) * wpr + 2 * qq);
-        const int sh = (row & 1) * 4;
-        return pack_nibbles(v.x, sh) | (pack_nibbles(v.y, sh) << 16);
+        const int a = row & 7;
+        const int c0 = (row >> 3) + (qq & 3);
+        const uint32_t woff = uint32_t(c0) * uint32_t(wpt) + uint32_t(qq) * 8u;
+        const uint4 A0 = load_bits4<BITS_SMEM>(bits_g + woff, bits_sa + woff * 4u);
+        const uint4 A1 = load_bits4<BITS_SMEM>(bits_g + woff + 4, bits_sa + woff * 4u + 16u);
+        const uint4 B0 = load_bits4<BITS_SMEM>(bits_g + woff + wpt, bits_sa + (woff + wpt) * 4u);
+        const uint4 B1 = load_bits4<BITS_SMEM>(bits_g + woff + wpt + 4, bits_sa + (woff + wpt) * 4u + 16u);
+        const uint32_t A[8] = {A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w};
+        const uint32_t Bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
+        const int sh = 4 * a;
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t X = (a + i < 8) ? A[i] : Bv[i];
+            const uint32_t Y = __funnelshift_r(X, X, sh);           // nibble (a + i) & 7 -> nibble i
+            out |= Y & (0xfu << (4 * i));
+        }
+        return out;
     };
     int j = m - 1;           // token index on row i0
     int last_start = n;      // first row of token j+1 (exclusive end of token j)
@@ -484,24 +595,17 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             }
             qw_pref = qw;
         }
-        uint32_t Rh[32];
+        uint32_t myR = 0x80000000u;
         uint32_t R = 0x80000000u;    // one-hot position inside the window; bit 31 <-> column j
 #pragma unroll
         for (int t = 0; t < 32; t += 2) {
             const uint4 a = *reinterpret_cast<const uint4*>(winbuf + 2 * t);    // A_t, A_t >> 1, A_t+1, A_t+1 >> 1
-            Rh[t] = R;
+            myR = lane == t ? R : myR;
             R = bt_step(R, a.x, a.y);
-            Rh[t + 1] = R;
+            myR = lane == t + 1 ? R : myR;
             R = bt_step(R, a.z, a.w);
         }
-        // this lane's row: position after `lane` rows -- 5-level select tree over the chain values
-#pragma unroll
-        for (int lvl = 0; lvl < 5; ++lvl) {
-            const bool bit = (lane >> lvl) & 1;
-#pragma unroll
-            for (int i = 0; i < (16 >> lvl); ++i) Rh[i] = bit ? Rh[2 * i + 1] : Rh[2 * i];
-        }
-        const uint32_t myR = Rh[0];
+        __syncwarp();                                           // winbuf is rewritten by the next block
         const int col = j - __clz(myR);
         const uint32_t dec = __ballot_sync(0xffffffffu, (myR & win) != 0u);   // bit t: path leaves row i0-t diagonally
         if (row >= 0 && !(p.dbg & 1)) hard_b[size_t(row) * p.T2max + col] = 1;
@@ -514,7 +618,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             dur_b[col] = int64_t(next_start - row);
         }
         if (smask) last_start = i0 - (31 - __clz(smask));
-        j -= __popc(dec);                                   // rows < 1 contribute no bits
+        j -= __clz(R);                                      // R: position after the block's 32 rows (rows < 1 do not move it)
     }
     if (probe) p.probe[3] = clock64();
 }
@@ -523,40 +627,33 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
 // host side
 // ---------------------------------------------------------------------------------------
 
-static int g_opt_cols_per_lane = 0;
 static int g_opt_ring_rows = 0;
 static int g_opt_slots = 0;
 static int g_opt_dbg = 0;
+static int g_opt_bits_global = 0;
+static int g_opt_no_tma = 0;
+static int g_opt_cols = 0;     // accepted for compatibility with older tools; the kernel has one strip width
 
 int mas_set_option(const char* key, int value, int* prev) {
-    if (!strcmp(key, "mas.cols_per_lane")) { *prev = g_opt_cols_per_lane; g_opt_cols_per_lane = value; return 0; }
     if (!strcmp(key, "mas.ring_rows")) { *prev = g_opt_ring_rows; g_opt_ring_rows = value; return 0; }
     if (!strcmp(key, "mas.slots")) { *prev = g_opt_slots; g_opt_slots = value; return 0; }
     if (!strcmp(key, "mas.dbg")) { *prev = g_opt_dbg; g_opt_dbg = value; return 0; }
+    if (!strcmp(key, "mas.bits_global")) { *prev = g_opt_bits_global; g_opt_bits_global = value; return 0; }
+    if (!strcmp(key, "mas.no_tma")) { *prev = g_opt_no_tma; g_opt_no_tma = value; return 0; }
+    if (!strcmp(key, "mas.cols_per_lane")) { *prev = g_opt_cols; g_opt_cols = value; return 0; }
     return -1;
 }
 
 struct MasPlan {
-    int C, ns, slots, full_floats, last_floats[2], ring_rows, bits_pitch;
+    int ns, slots, nstg, wlast;
     bool bits_smem;
     size_t slot_bytes;
-    size_t bits_ws_words;  // per utterance, when !bits_smem
+    size_t bits_words;     // per utterance
 };
 
-static size_t slot_bytes_for(int ns, int strip_floats_total, int ring_rows, size_t bits_bytes) {
-    size_t off = kSlotHdr + (ns > 1 ? sizeof(float) * size_t(ns - 1) * kBnd : 0);
-    off += sizeof(float) * (size_t(ring_rows) * strip_floats_total + kSeg);
-    off += bits_bytes;
-    return (off + 127) & ~size_t(127);
-}
-
-template <int C> static void ring_geometry(int T2max, int ns, MasPlan* pl) {
-    const int W = 32 * C;
-    pl->full_floats = (W / kSeg) * box_width<C>(kNumBox - 1);
-    const int last_cols = T2max - (ns - 1) * W;
-    const int c0 = last_cols < kSeg ? last_cols : kSeg, c1 = last_cols - c0;
-    pl->last_floats[0] = box_width<C>(box_index<C>(c0));
-    pl->last_floats[1] = c1 > 0 ? box_width<C>(box_index<C>(c1)) : 0;
+static size_t bits_words_for(int T1max, int ns) {
+    const size_t nct = 2 * (size_t(T1max + 31 + kR - 1) / kR) + 1;   // 8-step words; + 1: the backtrack reads one past the last
+    return nct * size_t(ns) * 32;
 }
 
 static int mas_plan(int B, int T1max, int T2max, MasPlan* pl) {
@@ -565,44 +662,44 @@ static int mas_plan(int B, int T1max, int T2max, MasPlan* pl) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem_limit = 227 * 1024;
-    // C = 4 (128-column strips) halves the row step; use it while every strip warp still gets an SM
-    // sub-partition to itself, C = 8 (256-column strips) in the throughput regime
-    int C = g_opt_cols_per_lane;
-    if (C != 4 && C != 8) C = (int64_t(B) * ((T2max + 127) / 128) <= 4 * int64_t(sm_count)) ? 4 : 8;
-    if (C == 4 && (T2max + 127) / 128 > kMaxStrips) C = 8;
-    const int W = 32 * C;
-    const int ns = (T2max + W - 1) / W;
+    const int ns = (T2max + kW - 1) / kW;
     if (ns > kMaxStrips) return ISP_ERR_UNSUPPORTED;
-    pl->C = C;
     pl->ns = ns;
-    if (C == 8) ring_geometry<8>(T2max, ns, pl); else ring_geometry<4>(T2max, ns, pl);
-    const int floats_total = (ns - 1) * pl->full_floats + pl->last_floats[0] + pl->last_floats[1];
-    pl->bits_pitch = ns * 32;
-    const size_t bits_bytes = size_t(C == 8 ? T1max : (T1max + 1) / 2) * pl->bits_pitch;
+    pl->wlast = (T2max - (ns - 1) * kW + 7) & ~7;
+    pl->bits_words = bits_words_for(T1max, ns);
+    const size_t bits_bytes = pl->bits_words * 4;
+    const size_t stage_bytes = size_t(kR) * size_t((ns - 1) * kW + pl->wlast) * 4;
+    const size_t fixed = kSlotHdr + (ns > 1 ? 4 * size_t(ns - 1) * kBnd : 0) + kZeroPage;
     // one utterance per CTA while every utterance still gets its own SM; two beyond that, so
     // that co-resident chains sit on different sub-partitions of one SM
     int slots = g_opt_slots > 0 ? g_opt_slots : (B > sm_count ? 2 : 1);
     if (slots > kMaxSlots) slots = kMaxSlots;
-    while (slots > 1 && 32 * slots * (ns + 1) > kMaxThreads) --slots;
+    while (slots > 1 && 32 * slots * (2 * ns + 1) > kMaxThreads) --slots;
+    if (slots > 1 && 2 * ns > 4) slots = 1;        // more strip warps than sub-partitions: co-residency buys nothing
     for (;; --slots) {
-        const size_t budget = smem_limit / slots;
-        for (int in_smem = 1; in_smem >= 0; --in_smem) {
-            const size_t fixed = slot_bytes_for(ns, floats_total, 0, in_smem ? bits_bytes : 0);
-            if (fixed + size_t(kMinRing) * floats_total * 4 > budget) continue;
-            int rows = int((budget - fixed - 128) / (size_t(floats_total) * 4));
-            rows = rows / kR * kR;
-            if (rows > kR * kMaxStages) rows = kR * kMaxStages;
-            if (in_smem && rows < 72 && slots == 1 && bits_bytes > 64 * 1024) continue;   // long utterances: prefer a deeper ring over resident bits
+        const size_t budget = (smem_limit / slots) & ~size_t(127);
+        int stg[2] = {0, 0};                      // [0]: bits in the workspace, [1]: bits in shared memory
+        for (int in_smem = 0; in_smem < 2; ++in_smem) {
+            const size_t need = fixed + (in_smem ? bits_bytes : 0);
+            if (need + kMinStages * stage_bytes > budget) continue;
+            size_t k = (budget - need) / stage_bytes;
+            stg[in_smem] = int(k > kMaxStages ? kMaxStages : k);
+        }
+        // resident bits save the backtrack an L2 round trip per block; a ring shallower than 8 stages (4 of them
+        // live) starves the chain
+        int in_smem = stg[1] >= 8 || (stg[1] > 0 && stg[1] >= stg[0]) ? 1 : 0;
+        if (g_opt_bits_global && stg[0] > 0) in_smem = 0;
+        int nstg = stg[in_smem];
+        if (nstg > 0) {
             if (g_opt_ring_rows > 0) {
-                int want = (g_opt_ring_rows + kR - 1) / kR * kR;
-                if (want < kMinRing) want = kMinRing;
-                if (want < rows) rows = want;
+                int want = (g_opt_ring_rows + kR - 1) / kR;
+                if (want < kMinStages) want = kMinStages;
+                if (want < nstg) nstg = want;
             }
             pl->slots = slots;
-            pl->ring_rows = rows;
+            pl->nstg = nstg;
             pl->bits_smem = in_smem != 0;
-            pl->slot_bytes = slot_bytes_for(ns, floats_total, rows, in_smem ? bits_bytes : 0);
-            pl->bits_ws_words = in_smem ? 0 : bits_bytes / 4;
+            pl->slot_bytes = (fixed + size_t(nstg) * stage_bytes + (in_smem ? bits_bytes : 0) + 127) & ~size_t(127);
             return 0;
         }
         if (slots == 1) break;
@@ -610,12 +707,12 @@ static int mas_plan(int B, int T1max, int T2max, MasPlan* pl) {
     return ISP_ERR_UNSUPPORTED;
 }
 
-// tensor maps over the logits: (T2max, T1max, B) fp32, box = (width, kR rows, 1), no swizzle
+// tensor maps over the logits: (T2max, T1max, B) fp32, box = (8 i columns, kR rows, 1), no swizzle
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool make_maps(MasMaps* maps, int C, const float* logp, int64_t sB, int64_t sT1, int B, int T1max, int T2max) {
+static bool make_maps(MasMaps* maps, const float* logp, int64_t sB, int64_t sT1, int B, int T1max, int T2max) {
     static PFN_encodeTiled enc = nullptr;
     if (!enc) {
         void* ptr = nullptr;
@@ -628,7 +725,7 @@ static bool make_maps(MasMaps* maps, int C, const float* logp, int64_t sB, int64
     cuuint64_t strides[2] = {cuuint64_t(sT1) * 4, cuuint64_t(B > 1 ? sB : sT1 * T1max) * 4};
     cuuint32_t estr[3] = {1, 1, 1};
     for (int i = 0; i < kNumBox; ++i) {
-        cuuint32_t box[3] = {cuuint32_t(C == 8 ? box_width<8>(i) : box_width<4>(i)), cuuint32_t(kR), 1};
+        cuuint32_t box[3] = {cuuint32_t(8 * (i + 1)), cuuint32_t(kR), 1};
         CUresult r = enc(&maps->m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(logp), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -639,19 +736,18 @@ static bool make_maps(MasMaps* maps, int C, const float* logp, int64_t sB, int64
 
 size_t mas_workspace_bytes(int B, int T1max, int T2max) {
     if (B <= 0 || T1max <= 0 || T2max <= 0) return 0;
-    // one bit per cell, rows padded to whole strips of either width, row pairs rounded up
-    const size_t words = (size_t(T1max) + 1) * ((size_t(T2max) + 255) / 256) * 8;
-    return 256 + size_t(B) * words * 4;
+    const int ns = (T2max + kW - 1) / kW;
+    return 256 + size_t(B) * bits_words_for(T1max, ns) * 4;
 }
 
-template <int C, bool BS, bool MULTI>
+template <bool BS, bool MULTI>
 static int launch_one(const MasMaps& maps, const MasParams& p, const MasPlan& pl, cudaStream_t stream) {
-    auto kern = mas_kernel<C, BS, MULTI>;
+    auto kern = mas_kernel<BS, MULTI>;
     const size_t smem = pl.slot_bytes * pl.slots;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mas_kernel)");
     const int grid = (p.B + pl.slots - 1) / pl.slots;
-    kern<<<grid, 32 * pl.slots * (pl.ns + 1), smem, stream>>>(maps, p);
+    kern<<<grid, 32 * pl.slots * (2 * pl.ns + 1), smem, stream>>>(maps, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mas_kernel launch");
     return 0;
@@ -684,26 +780,18 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
     p.status = reinterpret_cast<int*>(ws);
     p.probe = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 64);
     p.bits_ws = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 256);
-    p.bits_stride = int64_t(pl.bits_ws_words);
-    p.ns = pl.ns; p.slots = pl.slots; p.full_floats = pl.full_floats;
-    p.last_floats[0] = pl.last_floats[0]; p.last_floats[1] = pl.last_floats[1];
-    p.ring_rows = pl.ring_rows; p.bits_pitch = pl.bits_pitch; p.dbg = g_opt_dbg;
-    p.slot_bytes = int(pl.slot_bytes);
+    p.bits_stride = int64_t(pl.bits_words);
+    p.ns = pl.ns; p.slots = pl.slots; p.nstg = pl.nstg; p.wlast = pl.wlast;
+    p.slot_bytes = int(pl.slot_bytes); p.dbg = g_opt_dbg;
     MasMaps maps;
     memset(&maps, 0, sizeof(maps));
-    p.tma = make_maps(&maps, pl.C, logp, sB, sT1, B, T1max, T2max) ? 1 : 0;
+    p.tma = (!g_opt_no_tma && make_maps(&maps, logp, sB, sT1, B, T1max, T2max)) ? 1 : 0;
 
     cudaError_t e = cudaMemsetAsync(ws, 0, 256, stream);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(status)");
 
-#define ISP_MAS_DISPATCH(CC)                                                                          \
-    if (pl.bits_smem) return pl.ns > 1 ? launch_one<CC, true, true>(maps, p, pl, stream)             \
-                                       : launch_one<CC, true, false>(maps, p, pl, stream);           \
-    return pl.ns > 1 ? launch_one<CC, false, true>(maps, p, pl, stream)                              \
-                     : launch_one<CC, false, false>(maps, p, pl, stream);
-    if (pl.C == 4) { ISP_MAS_DISPATCH(4) }
-    ISP_MAS_DISPATCH(8)
-#undef ISP_MAS_DISPATCH
+    if (pl.bits_smem) return pl.ns > 1 ? launch_one<true, true>(maps, p, pl, stream) : launch_one<true, false>(maps, p, pl, stream);
+    return pl.ns > 1 ? launch_one<false, true>(maps, p, pl, stream) : launch_one<false, false>(maps, p, pl, stream);
 }
 
 }  // namespace isp

@@ -34,8 +34,19 @@ def assert_same(hard, dur, ref_hard, ref_dur, what=""):
 @pytest.fixture(autouse=True)
 def _reset_options():
     yield
-    _lib.set_option("mas.cols_per_lane", 0)
-    _lib.set_option("mas.ring_rows", 0)
+    for key in ("mas.ring_rows", "mas.slots", "mas.bits_global", "mas.no_tma"):
+        _lib.set_option(key, 0)
+
+
+# kernel variants: backpointer bits in shared memory or in the workspace, tiled TMA or 4 B async copies,
+# one or two utterances per CTA
+MODES = {"auto": {}, "bits_global": {"mas.bits_global": 1}, "no_tma": {"mas.no_tma": 1},
+         "two_slots": {"mas.slots": 2}, "two_slots_global_no_tma": {"mas.slots": 2, "mas.bits_global": 1, "mas.no_tma": 1}}
+
+
+def set_mode(mode):
+    for key, val in MODES[mode].items():
+        _lib.set_option(key, val)
 
 
 def test_known_answers(cuda_device):
@@ -51,10 +62,10 @@ def test_known_answers(cuda_device):
         assert np.array_equal(dur[0], ref.sum(0)), name
 
 
-@pytest.mark.parametrize("cols", [0, 4, 8])
-def test_cfg1_single_utterance(cuda_device, cols):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_cfg1_single_utterance(cuda_device, mode):
     """BASELINE.json configs[0]: 80 tokens x 400 frames, reference maximum path, bit-exact."""
-    _lib.set_option("mas.cols_per_lane", cols)
+    set_mode(mode)
     g = golden("mas_cfg1.npz")
     hard, dur, xt = run_cuda(g["x"], g["text_len"], g["mel_len"], cuda_device)
     assert np.array_equal(omas.path_from_hard(hard, g["mel_len"]), g["path"])
@@ -62,19 +73,19 @@ def test_cfg1_single_utterance(cuda_device, cols):
     assert np.array_equal(xt.cpu().numpy(), g["x"])          # input untouched
 
 
-@pytest.mark.parametrize("cols", [4, 8])
-def test_ragged_batch_with_ties(cuda_device, cols):
-    _lib.set_option("mas.cols_per_lane", cols)
+@pytest.mark.parametrize("mode", list(MODES))
+def test_ragged_batch_with_ties(cuda_device, mode):
+    set_mode(mode)
     g = golden("mas_ragged_ties.npz")
     hard, dur, _ = run_cuda(g["x"], g["text_len"], g["mel_len"], cuda_device)
     assert_same(hard, dur, g["hard"], g["hard"].sum(axis=1, dtype=np.int64), "ragged_ties")
     assert np.array_equal(dur.sum(1), g["mel_len"])
 
 
-@pytest.mark.parametrize("cols", [4, 8])
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("tag", ["cfg2_noise", "cfg2_ties", "odd_shapes", "wide", "long"])
-def test_seeded_golden(cuda_device, tag, cols):
-    _lib.set_option("mas.cols_per_lane", cols)
+def test_seeded_golden(cuda_device, tag, mode):
+    set_mode(mode)
     g = golden(f"mas_seeded_{tag}.npz")
     B, T1, T2 = int(g["B"]), int(g["T1"]), int(g["T2"])
     x = synth.noise_logits(B, T1, T2, int(g["seed"]), quantize=float(g["quantize"]))
@@ -86,17 +97,17 @@ def test_seeded_golden(cuda_device, tag, cols):
         assert hard[b, int(g["mel_len"][b]):].sum() == 0 and hard[b, :, int(g["text_len"][b]):].sum() == 0
 
 
-@pytest.mark.parametrize("ring", [48, 56, 80])
+@pytest.mark.parametrize("ring", [80, 96, 128])
 def test_small_ring_wraparound(cuda_device, ring):
     """Few rows in flight: every ring stage is reused many times."""
-    _lib.set_option("mas.ring_rows", ring)
-    x = synth.noise_logits(9, 257, 130, 5, quantize=0.25)
-    tl, ml = synth.lengths(9, 130, 257, True, 5)
-    for cols in (4, 8):
-        _lib.set_option("mas.cols_per_lane", cols)
+    x = synth.noise_logits(9, 257, 132, 5, quantize=0.25)
+    tl, ml = synth.lengths(9, 132, 257, True, 5)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    for mode in ("auto", "no_tma", "two_slots"):
+        set_mode(mode)
+        _lib.set_option("mas.ring_rows", ring)
         hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
-        rh, rd = omas.b_mas_with_durations(x, tl, ml)
-        assert_same(hard, dur, rh, rd, f"ring={ring} cols={cols}")
+        assert_same(hard, dur, rh, rd, f"ring={ring} mode={mode}")
 
 
 def test_full_size_cfg3_against_oracle(cuda_device):
@@ -122,22 +133,22 @@ def test_full_size_cfg4_long_form(cuda_device):
     w = synth.WORKLOADS["cfg4"]
     tl, ml = synth.workload_lengths(w)
     x = synth.noise_logits(w.batch, w.t1max, w.t2max, w.seed)
-    for cols in (4, 8):
-        _lib.set_option("mas.cols_per_lane", cols)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    for mode in ("auto", "no_tma"):
+        set_mode(mode)
         hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
-        rh, rd = omas.b_mas_with_durations(x, tl, ml)
-        assert_same(hard, dur, rh, rd, f"cfg4 cols={cols}")
+        assert_same(hard, dur, rh, rd, f"cfg4 mode={mode}")
 
 
 def test_maximum_width(cuda_device):
-    T2 = 1024                                             # ISP_MAS_MAX_T2
+    T2 = 640                                              # ISP_MAS_MAX_T2
     x = synth.noise_logits(2, 300, T2, 11, quantize=0.5)
-    tl, ml = np.array([1024, 700]), np.array([300, 211])
+    tl, ml = np.array([640, 450]), np.array([300, 211])
     hard, dur, _ = run_cuda(x, tl, ml, cuda_device)       # text longer than mel: pure diagonal tail
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
-    assert_same(hard, dur, rh, rd, "T2=1024")
+    assert_same(hard, dur, rh, rd, "T2=640")
     with pytest.raises(_lib.IspError):
-        mas_forward(torch.zeros(1, 4, 1025, device=cuda_device), torch.tensor([1025]), torch.tensor([4]))
+        mas_forward(torch.zeros(1, 4, 641, device=cuda_device), torch.tensor([641]), torch.tensor([4]))
 
 
 def test_unaligned_and_strided_inputs(cuda_device):

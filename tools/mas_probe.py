@@ -12,13 +12,13 @@ import torch
 from isp_tts_b200 import _lib, synth
 
 
-def run(name, ring=0, slots=0, dbg=0, cols=0):
+def run(name, ring=0, slots=0, dbg=0, bits_global=0):
     w = synth.WORKLOADS[name]
     lib = _lib.load()
     _lib.set_option("mas.ring_rows", ring)
     _lib.set_option("mas.slots", slots)
     _lib.set_option("mas.dbg", dbg)
-    _lib.set_option("mas.cols_per_lane", cols)
+    _lib.set_option("mas.bits_global", bits_global)
     dev = torch.device("cuda:0")
     tl, ml = synth.workload_lengths(w)
     # utterance 0 is the one that is probed: make it the longest so that the chain is visible
@@ -42,11 +42,11 @@ def run(name, ring=0, slots=0, dbg=0, cols=0):
         torch.cuda.synchronize()
         assert rc == 0, lib.isp_last_error()
         times.append(s.elapsed_time(e) * 1e3)
-    pr = ws[64:112].view(torch.int64).cpu().numpy()
+    pr = ws[64:128].view(torch.int64).cpu().numpy()
     n = int(ml[0])
-    print(f"{name} cols={cols} ring={ring} slots={slots} dbg={dbg}: kernel {min(times):.1f} us (median {np.median(times):.1f}); utterance 0 ({n} x {int(tl[0])}): "
+    print(f"{name} bits_global={bits_global} ring={ring} slots={slots} dbg={dbg}: kernel {min(times):.1f} us (median {np.median(times):.1f}); utterance 0 ({n} x {int(tl[0])}): "
           f"forward {pr[1]-pr[0]} cyc ({(pr[1]-pr[0])/(n+31):.1f}/step), barrier {pr[2]-pr[1]}, "
-          f"backtrack {pr[3]-pr[2]} cyc ({(pr[3]-pr[2])/n:.1f}/row); in issue {pr[4]} cyc, in wait {pr[5]} cyc", flush=True)
+          f"backtrack {pr[3]-pr[2]} cyc ({(pr[3]-pr[2])/n:.1f}/row); waiting for logits {pr[4]} cyc, for the neighbour strip {pr[5]} cyc; loader: {pr[7]} cyc of which waiting for free stages {pr[6]}", flush=True)
 
 
 rings = [int(c) for c in os.environ.get("PROBE_RING", "0").split(",")]
@@ -55,5 +55,5 @@ for name in sys.argv[1:] or ["cfg2", "cfg3"]:
     for r in rings:
         for sl in slots:
             for d in [int(c) for c in os.environ.get("PROBE_DBG", "0").split(",")]:
-                for c in [int(c) for c in os.environ.get("PROBE_COLS", "0").split(",")]:
+                for c in [int(c) for c in os.environ.get("PROBE_BITS_GLOBAL", "0").split(",")]:
                     run(name, r, sl, d, c)
