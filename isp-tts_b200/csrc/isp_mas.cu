@@ -116,6 +116,19 @@ ISP_DEVINL int ld_volatile_sa(uint32_t saddr) {
     asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
     return v;
 }
+// predicated forms: a divergent `if (lane == ...)` around one instruction costs BSSY/BSYNC and a branch
+ISP_DEVINL void mbar_arrive_if_sa(uint32_t bar, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 st;\n\tsetp.ne.u32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
+                 ::"r"(bar), "r"(uint32_t(pred)) : "memory");
+}
+ISP_DEVINL void st_volatile_if_sa(uint32_t saddr, int v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.volatile.shared::cta.s32 [%0], %1;\n\t}"
+                 ::"r"(saddr), "r"(v), "r"(uint32_t(pred)) : "memory");
+}
+ISP_DEVINL void sts_f32_if(uint32_t saddr, float v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}"
+                 ::"r"(saddr), "f"(v), "r"(uint32_t(pred)) : "memory");
+}
 ISP_DEVINL void st_volatile_sa(uint32_t saddr, int v) {
     asm volatile("st.volatile.shared::cta.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -247,6 +260,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     const uint32_t empty_sa = sm_sa + 1024;                                     // [kMaxStrips][kMaxStages] u64: stage may be refilled
     const uint32_t prog_sa = sm_sa + 2048;                                      // [kMaxStrips] chunks whose last column strip s has published
     const uint32_t cons_sa = prog_sa + 4 * kMaxStrips;                          // [kMaxStrips] chunks whose boundary values strip s has taken
+    const uint32_t landed_sa = cons_sa + 4 * kMaxStrips;                        // [kMaxStrips] chunks of logits that have landed in strip s's ring
     uint32_t* winbuf = reinterpret_cast<uint32_t*>(sm + 2304);                  // [32][2] backtrack windows (A, A >> 1)
     uint32_t off = kSlotHdr;
     const uint32_t bnd_sa = sm_sa + off;                                        // [ns-1][kBnd] floats
@@ -268,7 +282,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     const int nch = (n + 31 + kR - 1) / kR;                             // chunks of a strip's n + 31 steps
     const bool probe_w = p.probe != nullptr && b == 0 && s == 0;        // warp-uniform
     const bool probe = probe_w && is_strip && lane == 0;
-    long long pc_full = 0, pc_flag = 0;
+    long long pc_full = 0, pc_flag = 0, pc_loop = 0, pc_nloop = 0;
 
     // per strip: the utterance's columns, the TMA box / ring row width and the ring
     const int mcols = max(0, min(kW, m - s * kW));
@@ -289,6 +303,8 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             }
             reinterpret_cast<int*>(sm + 2048)[s] = 0;
             reinterpret_cast<int*>(sm + 2048)[kMaxStrips + s] = 0;
+            reinterpret_cast<int*>(sm + 2048)[2 * kMaxStrips + s] = 0;
+            if (s == 0) for (int i = 0; i < 3; ++i) mbar_init(reinterpret_cast<uint64_t*>(sm + 960) + i, 1);
             fence_mbar_init();
         }
     } else if (role == 2) {
@@ -309,46 +325,54 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             // producer's step index -- chunk-aligned for the writer; the reader's 16 rows straddle two chunks (15 | 0..14)
             const uint32_t bnd_mine = bnd_sa + uint32_t(s) * kBnd * 4u;
             const uint32_t bnd_prev = bnd_sa + uint32_t(s > 0 ? s - 1 : 0) * kBnd * 4u;
+            const uint32_t landed_s = landed_sa + 4u * s;
             const float qnan = __int_as_float(0x7fffffff);
             const int gcol0 = s * kW + lane * kC;
+            const bool lane0 = lane == 0;
 
             float q[kC], xc[kC];
 #pragma unroll
             for (int c = 0; c < kC; ++c) q[c] = -CUDART_INF_F;
             float left_cur = qnan;
+            float bvals[kR];                                        // left neighbours of lane 0's next 16 rows (NaN: there is none)
+#pragma unroll
+            for (int k = 0; k < kR; ++k) bvals[k] = qnan;
 
             // ring row (byte offset inside the ring) this lane reads next: row (t + 1 - lane) mod ring at step t
             uint32_t rd = (uint32_t(nstg * kR) - uint32_t(lane)) * pitchB;
             if (rd >= ringB) rd -= ringB;
-            mbar_wait_sa(full_s, 0);                                   // chunk 0
+            int landed_seen = 0, l_early = 0;
+            {
+                uint32_t spins = 0;
+                while ((landed_seen = ld_acquire_sa(landed_s)) < 1) { if (++spins > (1u << 26)) __trap(); }   // chunk 0
+            }
             lds_row(xc, lane_ring + rd);                               // the row of step 0
             rd += pitchB; if (rd >= ringB) rd -= ringB;
-            int st_wait = 1;                                           // stage of chunk ch + 1
-            uint32_t ph_wait = 0u;
             int st_free = 0;                                           // stage of chunk ch - 3
             int st_cur = 0;                                            // stage of chunk ch
             uint32_t bits_off = uint32_t(s * 32 + lane) * 4u;          // byte offset of this lane's first word of chunk ch
             int prog_seen = 0, cons_seen = 0, p_early = 0, c_early = 0;
 
+            // All waits below are on plain shared counters, read one chunk (or half a chunk) before they are looked at:
+            // an mbarrier test costs the warp ~100 cycles even when the phase is long complete, an acquire load ~70.
+            // Branches on them are made warp-uniform with a vote, which keeps the common path free of divergence handling.
             for (int ch = 0; ch < nch; ++ch) {
                 const int t0 = ch * kR;
-                // ---- chunk top: free the stage whose last reader has moved on ----
-                if (ch >= 3) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_sa(empty_s + uint32_t(st_free) * 8u);
-                    st_free = st_free + 1 == nstg ? 0 : st_free + 1;
-                }
-                const bool wait_next = ch + 1 < nch;                   // lane 0's read-ahead crosses into the next stage on the last step
-                float bvals[kR];
-#pragma unroll
-                for (int k = 0; k < kR; ++k) bvals[k] = qnan;
+                // ---- chunk top: free the stage whose last reader has moved on (chunk ch - 3) ----
+                __syncwarp();
+                mbar_arrive_if_sa(empty_s + uint32_t(st_free) * 8u, lane0 && ch >= 3);
+                st_free = ch >= 3 ? (st_free + 1 == nstg ? 0 : st_free + 1) : 0;
+                // lane 0's read-ahead crosses into the next stage on the last step: chunk ch + 1 must have landed by then
+                const int need_landed = min(ch + 2, nch);
+                landed_seen = max(landed_seen, l_early);
+                l_early = ld_volatile_sa(landed_s);
                 uint32_t pub_sa = 0;
                 if (MULTI) {
                     if (has_prev) {
                         // the boundary values of rows t0 .. t0+15: the producer must have published its chunks <= ch + 2
                         const int need = min(ch + 3, nch);
                         prog_seen = max(prog_seen, p_early);
-                        if (prog_seen < need) {
+                        if (__any_sync(0xffffffffu, prog_seen < need)) {
                             long long c0 = 0;
                             if (probe_w) c0 = clock64();
                             uint32_t spins = 0;
@@ -367,13 +391,13 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
                         bvals[9] = __uint_as_float(u2.x); bvals[10] = __uint_as_float(u2.y); bvals[11] = __uint_as_float(u2.z); bvals[12] = __uint_as_float(u2.w);
                         bvals[13] = __uint_as_float(u3.x); bvals[14] = __uint_as_float(u3.y); bvals[15] = __uint_as_float(u3.z);
                         p_early = ld_volatile_sa(prog_sa + 4u * (s - 1));   // looked at one chunk from now
-                        if (lane == 0) st_volatile_sa(cons_sa + 4u * s, ch); // the values of chunks < ch are in registers
+                        st_volatile_if_sa(cons_sa + 4u * s, ch, lane0);      // the values of chunks < ch are in registers
                     }
                     if (has_next) {
                         // this chunk overwrites the slots written 8 chunks ago, which the reader takes in its chunks <= ch - 9
                         const int need = ch - 8;
                         cons_seen = max(cons_seen, c_early);
-                        if (cons_seen < need) {
+                        if (__any_sync(0xffffffffu, cons_seen < need)) {
                             long long c0 = 0;
                             if (probe_w) c0 = clock64();
                             uint32_t spins = 0;
@@ -388,15 +412,23 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
                     }
                 }
                 uint32_t word0, word1;
-                const bool steady = t0 >= 32 && t0 + kR <= n;
-                // one step; WRAP: the ring may wrap inside the chunk for some lanes; EDGE: some lanes are before row 0 or past row n-1
-#define ISP_MAS_STEP(WRAP, EDGE)                                                                                   \
+                {
+                    // one step; WRAP: the ring may wrap inside the chunk for some lanes; HEAD: some lane starts its row 0 here.
+                    // Rows past n - 1 need no special case: what the lanes compute there is never stored or consumed.
+#define ISP_MAS_STEP(WRAP, HEAD)                                                                                   \
                     {                                                                                              \
-                        if (k == 8 && wait_next) {                                                                 \
-                            long long c0 = 0;                                                                      \
-                            if (probe_w) c0 = clock64();                                                           \
-                            mbar_wait_sa(full_s + uint32_t(st_wait) * 8u, ph_wait);                                \
-                            if (probe_w) pc_full += clock64() - c0;                                                \
+                        if (k == 8) {                                                                              \
+                            landed_seen = max(landed_seen, l_early);                                               \
+                            if (__any_sync(0xffffffffu, landed_seen < need_landed)) {                              \
+                                long long c0 = 0;                                                                  \
+                                if (probe_w) c0 = clock64();                                                       \
+                                uint32_t spins = 0;                                                                \
+                                do {                                                                               \
+                                    landed_seen = ld_acquire_sa(landed_s);                                         \
+                                    if (++spins > (1u << 26)) __trap();                                            \
+                                } while (landed_seen < need_landed);                                               \
+                                if (probe_w) pc_full += clock64() - c0;                                            \
+                            }                                                                                      \
                         }                                                                                          \
                         const float nxt = __shfl_up_sync(0xffffffffu, q[kC - 1], 1);                               \
                         float xn[kC];                                                                              \
@@ -404,33 +436,37 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
                         rd += pitchB;                                                                              \
                         if (WRAP) { if (rd >= ringB) rd -= ringB; }                                                \
                         const float v = dp_row(q, xc, left_cur);                                                   \
-                        if (EDGE) {                                                                                \
-                            if (t0 + k - lane == 0) {                                                              \
+                        if (HEAD) {                                                                                \
+                            if (t0 + k == lane) {                                                                  \
                                 /* row 0: Q[0][0] = x[0][0], Q[0][j>0] = -inf   (mas.py:11) */                     \
                                 _Pragma("unroll") for (int c = 0; c < kC; ++c) q[c] = (gcol0 + c == 0) ? xc[c] : -CUDART_INF_F; \
                             }                                                                                      \
                         }                                                                                          \
                         acc[k >> 2] = fmaf(v, float(1 << (4 * (k & 3))), acc[k >> 2]);                             \
-                        if (MULTI && pub) sts_f32(pub_sa + uint32_t(k) * 4u, q[kC - 1]);   /* rows outside [0, n) are never consumed */ \
-                        left_cur = lane == 0 ? bvals[k] : nxt;                                                     \
+                        if (MULTI) sts_f32_if(pub_sa + uint32_t(k) * 4u, q[kC - 1], pub);                          \
+                        left_cur = lane0 ? bvals[k] : nxt;                                                         \
                         _Pragma("unroll") for (int c = 0; c < kC; ++c) xc[c] = xn[c];                              \
                     }
-                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (steady && st_cur >= 2 && st_cur + 1 < nstg) {
-                    // the lanes read rows t0 - 30 .. t0 + 16, i.e. stages st_cur - 2 .. st_cur + 1: no wrap
+                    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    long long cl0 = 0;
+                    if (probe_w) cl0 = clock64();
+                    if (ch < 2) {
 #pragma unroll
-                    for (int k = 0; k < kR; ++k) ISP_MAS_STEP(false, false)
-                } else if (steady) {
+                        for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, true)
+                    } else if (st_cur >= 2 && st_cur + 1 < nstg) {
+                        // the lanes read rows t0 - 30 .. t0 + 16, i.e. stages st_cur - 2 .. st_cur + 1: no wrap
 #pragma unroll
-                    for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, false)
-                } else {
+                        for (int k = 0; k < kR; ++k) ISP_MAS_STEP(false, false)
+                        if (rd >= ringB) rd -= ringB;                  // the chunk may end exactly on the ring's end
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, true)
-                }
+                        for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, false)
+                    }
 #undef ISP_MAS_STEP
-                if (rd >= ringB) rd -= ringB;                          // the no-wrap chunk may end exactly on the ring's end
-                word0 = __byte_perm(__float_as_uint(acc[0] + 8388608.0f), __float_as_uint(acc[1] + 8388608.0f), 0x5410);
-                word1 = __byte_perm(__float_as_uint(acc[2] + 8388608.0f), __float_as_uint(acc[3] + 8388608.0f), 0x5410);
+                    if (probe_w) { pc_loop += clock64() - cl0; pc_nloop += 1; }
+                    word0 = __byte_perm(__float_as_uint(acc[0] + 8388608.0f), __float_as_uint(acc[1] + 8388608.0f), 0x5410);
+                    word1 = __byte_perm(__float_as_uint(acc[2] + 8388608.0f), __float_as_uint(acc[3] + 8388608.0f), 0x5410);
+                }
                 if (BITS_SMEM) {
                     sts_u32(bits_sa + bits_off, word0);
                     sts_u32(bits_sa + bits_off + uint32_t(wpt) * 4u, word1);
@@ -440,8 +476,8 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
                 }
                 bits_off += uint32_t(wpt) * 8u;
                 st_cur = st_cur + 1 == nstg ? 0 : st_cur + 1;
-                if (wait_next) { if (++st_wait == nstg) { st_wait = 0; ph_wait ^= 1u; } }
-                if (MULTI && pub) st_release_sa(prog_sa + 4u * s, ch + 1);   // releases this lane's 16 stores
+                // the publishing lane's 16 stores precede this one in program order; shared memory keeps a thread's stores in order
+                if (MULTI) st_volatile_if_sa(prog_sa + 4u * s, ch + 1, pub);
             }
         }
     } else if (role == 1) {
@@ -453,39 +489,53 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             const uint64_t pol = policy_evict_first();
             const CUtensorMap* map = &maps.m[wb / 8 - 1];
             const float* src_b = p.logp + int64_t(b) * p.sB + s * kW;
-            int st = 0;
-            uint32_t ph = 1u;                                         // parity to wait for on empty[st]: phase (c / nstg - 1)
-            for (int c = 0; c < nch; ++c) {
-                const uint32_t full_b = full_s + uint32_t(st) * 8u;
-                if (c >= nstg) {
-                    long long c0 = 0;
-                    if (lprobe) c0 = clock64();
-                    if (p.tma) { if (lane == 0) mbar_wait_idle_sa(empty_s + uint32_t(st) * 8u, ph); }
-                    else mbar_wait_idle_sa(empty_s + uint32_t(st) * 8u, ph);
-                    if (lprobe) lp_wait += clock64() - c0;
-                }
-                const int r0 = kR * c;
-                const uint32_t dst = ring_s + uint32_t(st) * stageB;
-                if (p.tma) {
-                    if (lane == 0) {
-                        if (r0 < n && !(p.dbg & 8)) {
-                            mbar_expect_tx_sa(full_b, stageB);
-                            tma_load_box(dst, map, s * kW, r0, b, full_b, pol);
+            // Two cursors over the chunks: `issued` (gated by the strip's "empty" arrivals) and `landed` (the "full"
+            // barriers, turned into the plain counter the strip polls).  mbarrier tests cost ~100 cycles of this warp only.
+            const bool solo = p.tma != 0;                              // TMA: one lane does everything
+            if (!solo || lane == 0) {
+                int issued = 0, landed = 0, st_i = 0, st_l = 0;
+                uint32_t ph_i = 1u, ph_l = 0u;                         // empty[st_i]: phase (issued / nstg - 1);  full[st_l]: phase (landed / nstg)
+                uint32_t idle = 0;
+                while (landed < nch) {
+                    bool did = false;
+                    if (issued < nch && (issued < nstg || mbar_test_sa(empty_s + uint32_t(st_i) * 8u, ph_i))) {
+                        const uint32_t full_b = full_s + uint32_t(st_i) * 8u;
+                        const int r0 = kR * issued;
+                        const uint32_t dst = ring_s + uint32_t(st_i) * stageB;
+                        const bool fetch = r0 < n && !(p.dbg & 8);     // past the last row the strip's tail runs on stale rows
+                        if (solo) {
+                            if (fetch) {
+                                mbar_expect_tx_sa(full_b, stageB);
+                                tma_load_box(dst, map, s * kW, r0, b, full_b, pol);
+                            } else {
+                                mbar_arrive_sa(full_b);
+                            }
                         } else {
-                            mbar_arrive_sa(full_b);                   // nothing to fetch: the strip's tail runs on stale rows
+                            // unaligned base or strides: 4 B async copies, one column per lane and pass
+                            if (fetch) {
+                                const int rows = min(kR, n - r0);
+                                for (int r = 0; r < rows; ++r)
+                                    for (int col = lane; col < mcols; col += 32)
+                                        cp_async4(dst + uint32_t(r) * pitchB + uint32_t(col) * 4u, src_b + int64_t(r0 + r) * p.sT1 + col);
+                            }
+                            cp_async_arrive_noinc_sa(full_b);
                         }
+                        ++issued;
+                        if (++st_i == nstg) { st_i = 0; ph_i ^= 1u; }
+                        did = true;
                     }
-                } else {
-                    // unaligned base or strides: 4 B async copies, one column per lane and pass
-                    if (r0 < n && !(p.dbg & 8)) {
-                        const int rows = min(kR, n - r0);
-                        for (int r = 0; r < rows; ++r)
-                            for (int col = lane; col < mcols; col += 32)
-                                cp_async4(dst + uint32_t(r) * pitchB + uint32_t(col) * 4u, src_b + int64_t(r0 + r) * p.sT1 + col);
+                    if (landed < issued && mbar_test_sa(full_s + uint32_t(st_l) * 8u, ph_l)) {
+                        ++landed;
+                        if (++st_l == nstg) { st_l = 0; ph_l ^= 1u; }
+                        if (solo || lane == 0) st_release_sa(landed_sa + 4u * s, landed);
+                        did = true;
                     }
-                    cp_async_arrive_noinc_sa(full_b);
+                    if (!did) {
+                        __nanosleep(100);
+                        if (++idle > (1u << 24)) __trap();
+                        if (lprobe) lp_wait += 1;
+                    }
                 }
-                if (++st == nstg) { st = 0; ph ^= 1u; }
             }
             if (lprobe) { p.probe[6] = lp_wait; p.probe[7] = clock64() - lp_t0; }
         }
@@ -529,7 +579,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     }
 
     // bits (shared or global) and the zero-filled outputs become visible to the slot's warp 0
-    if (probe) { p.probe[1] = clock64(); p.probe[4] = pc_full; p.probe[5] = pc_flag; }
+    if (probe) { p.probe[1] = clock64(); p.probe[4] = pc_full; p.probe[5] = pc_flag; p.probe[8] = pc_loop; p.probe[9] = pc_nloop; }
     if (!BITS_SMEM) __threadfence_block();
     asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(slot_threads) : "memory");
     if (!is_strip || s != 0) return;
@@ -539,17 +589,53 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     // mas.py:20-24.  Rows i0, i0-1, ..., i0-31 per block; lane t owns row i0-t.
     int16_t* hard_b = p.hard + size_t(b) * p.T1max * p.T2max;
     int64_t* dur_b = p.dur ? p.dur + size_t(b) * p.T2max : nullptr;
+    // Bits in the workspace are staged through shared memory in pieces of 128 rows (the 20 word-rows [16 P, 16 P + 20)
+    // cover every lane's words of rows [128 P, 128 P + 128)): one bulk copy each, three slots laid over the idle ring.
+    constexpr int kPieceRows = 20;
+    const uint32_t pieceB = uint32_t(kPieceRows) * uint32_t(wpt) * 4u;
+    const uint32_t stg_sa = ring_sa;
+    const uint32_t sbar_sa = sm_sa + 960;                                  // 3 mbarriers in the unused tail of the "full" array
+    const int nct = 2 * ((p.T1max + 31 + kR - 1) / kR) + 1;                 // word-rows per utterance in the workspace
+    const int p_top = (n - 1) >> 7;
+    int p_issue = p_top;                                                   // next piece to stage (descending)
+    int p_waited = p_top + 1;                                              // pieces >= p_waited have landed
+    auto stage_piece = [&](int P) {
+        if (lane == 0) {
+            const int slot = (p_top - P) % 3;
+            const int rows = min(kPieceRows, nct - 16 * P);
+            const uint32_t bytes = uint32_t(rows) * uint32_t(wpt) * 4u;
+            mbar_expect_tx_sa(sbar_sa + uint32_t(slot) * 8u, bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(stg_sa + uint32_t(slot) * pieceB), "l"(bits_g + size_t(16 * P) * wpt), "r"(bytes), "r"(sbar_sa + uint32_t(slot) * 8u)
+                         : "memory");
+        }
+    };
+    auto ensure_pieces = [&](int pmin) {                                   // warp-uniform
+        while (p_waited > pmin) {
+            --p_waited;
+            const int use = (p_top - p_waited) / 3;
+            mbar_wait_sa(sbar_sa + uint32_t((p_top - p_waited) % 3) * 8u, uint32_t(use) & 1u);
+        }
+    };
+    if (!BITS_SMEM) {
+        fence_proxy_async();                                               // the ring was read and written through the generic proxy
+        for (int k = 0; k < 3 && p_issue >= 0; ++k) stage_piece(p_issue--);
+    }
     // The 32 backpointer bits of columns [32 qq, 32 qq + 32) of row `row`: global lane L = 8 qq + i holds row `row` in
     // the word of chunk (row + l) >> 3 (l = L mod 32) at nibble (row + l) & 7  ->  for i = 0..7 the nibble index runs
     // cyclically from a = row & 7 and the chunk steps once, where a + i reaches 8.
     auto bits_word = [&](int row, int qq) -> uint32_t {
         const int a = row & 7;
         const int c0 = (row >> 3) + (qq & 3);
-        const uint32_t woff = uint32_t(c0) * uint32_t(wpt) + uint32_t(qq) * 8u;
-        const uint4 A0 = load_bits4<BITS_SMEM>(bits_g + woff, bits_sa + woff * 4u);
-        const uint4 A1 = load_bits4<BITS_SMEM>(bits_g + woff + 4, bits_sa + woff * 4u + 16u);
-        const uint4 B0 = load_bits4<BITS_SMEM>(bits_g + woff + wpt, bits_sa + (woff + wpt) * 4u);
-        const uint4 B1 = load_bits4<BITS_SMEM>(bits_g + woff + wpt + 4, bits_sa + (woff + wpt) * 4u + 16u);
+        uint32_t base;
+        if (BITS_SMEM) {
+            base = bits_sa + (uint32_t(c0) * uint32_t(wpt) + uint32_t(qq) * 8u) * 4u;
+        } else {
+            const int P = row >> 7;
+            base = stg_sa + uint32_t((p_top - P) % 3) * pieceB + (uint32_t(c0 - 16 * P) * uint32_t(wpt) + uint32_t(qq) * 8u) * 4u;
+        }
+        const uint4 A0 = lds_v4(base), A1 = lds_v4(base + 16u);
+        const uint4 B0 = lds_v4(base + uint32_t(wpt) * 4u), B1 = lds_v4(base + uint32_t(wpt) * 4u + 16u);
         const uint32_t A[8] = {A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w};
         const uint32_t Bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
         const int sh = 4 * a;
@@ -568,6 +654,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     // candidate words of the NEXT block's window are fetched before the chain runs (j moves <= 32)
     uint32_t w0 = 0, w1 = 0, w2 = 0;
     int qw_pref = j >> 5;
+    if (!BITS_SMEM) ensure_pieces(max(n - 32, 0) >> 7);
     {
         const int row = n - 1 - lane;
         if (row >= 1) {
@@ -585,6 +672,14 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
         *reinterpret_cast<uint2*>(winbuf + 2 * lane) = make_uint2(win, win >> 1);
         __syncwarp();
         // prefetch for the block below: its j is in [j-32, j]  ->  word index in {qw, qw-1, qw-2}
+        if (!BITS_SMEM) {
+            // pieces above the rows still to be fetched are dead: refill their slots, then make sure this fetch's pieces are in
+            while (p_issue >= 0 && p_issue + 3 > ((i0 - 32) >> 7) && i0 >= 32) {
+                if (p_issue + 3 > p_top) break;                           // cannot happen: the first three were staged up front
+                stage_piece(p_issue--);
+            }
+            if (i0 >= 32) ensure_pieces(max(i0 - 63, 0) >> 7);
+        }
         {
             const int nrow = row - 32;
             w0 = w1 = w2 = 0u;
