@@ -91,6 +91,7 @@ struct MasParams {
     int64_t* dur;
     uint32_t* bits_ws;     // global backpointer bits (BITS_SMEM == false)
     int64_t bits_stride;   // words per utterance in bits_ws
+    int16_t* path_ws;      // (B, T1max) int16: the path's column per row, until the zero-fill has landed
     int* status;           // count of utterances with out-of-contract lengths
     long long* probe;      // clock64 stamps of utterance 0 (tools/mas_probe.py)
     int ns;                // strip warps per utterance
@@ -313,7 +314,10 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             reinterpret_cast<int*>(sm + 2048)[s] = 0;
             reinterpret_cast<int*>(sm + 2048)[kMaxStrips + s] = 0;
             reinterpret_cast<int*>(sm + 2048)[2 * kMaxStrips + s] = 0;
-            if (s == 0) for (int i = 0; i < 32; ++i) reinterpret_cast<int*>(sm + 2048 + 128)[i] = 0;   // converter / chain counters
+            if (s == 0) {
+                for (int i = 0; i < 32; ++i) reinterpret_cast<int*>(sm + 2048 + 128)[i] = 0;   // converter / chain counters
+                for (int i = 0; i < 2 * (2 * kMaxStrips - 1); ++i) mbar_init(reinterpret_cast<uint64_t*>(sm + 640) + i, 1);   // converter staging
+            }
             fence_mbar_init();
         }
     } else if (role == 2) {
@@ -568,23 +572,42 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             int64_t* d = p.dur + size_t(b) * p.T2max;
             for (int j = lane; j < p.T2max; j += 32) d[j] = 0;
         }
-        if (lane == 0) {
-            // spread the copies over ~80 % of the forward pass (~20 ns per row) so that they do not crowd out the first loads
-            const long long pieces = (long long)((size_t(ze - zb) + kZeroPage - 1) / kZeroPage);
-            long long gap = pieces > 0 ? (16LL * n - 65LL * pieces) / pieces : 0;
-            if (gap < 0 || (p.dbg & 16)) gap = 0;
-            if (gap > 2000) gap = 2000;
-            for (char* zp = zb; zp < ze;) {
-                const uint32_t bytes = uint32_t(min(size_t(kZeroPage), size_t(ze - zp)));
-                bulk_s2g(zp, zero_sa, bytes);
-                bulk_commit();
-                zp += bytes;
-                if (gap > 0) __nanosleep(unsigned(gap));
-            }
-            bulk_wait_all();                              // the zeros are in place before the backtrack writes its ones
-            fence_proxy_async();
-        }
+        // The filler takes no part in the backtrack: it announces itself at the slot's barrier now (its plain stores above are
+        // ordered before the barrier completes) and keeps filling while the others go on.
         __syncwarp();
+        asm volatile("bar.arrive %0, %1;" ::"r"(slot + 1), "r"(slot_threads) : "memory");
+        if (lane == 0) {
+            // The copies follow the slot's progress (chunks of logits landed for strip 0, then blocks of the backtrack done),
+            // so that they share HBM with the logit loads without running ahead of them, spill into the backtrack, when HBM
+            // is otherwise idle, and are complete shortly before the path's ones are due (fill_done).
+            const int pieces = int((size_t(ze - zb) + kZeroPage - 1) / kZeroPage);
+            const int nblk_f = (n + 31) >> 5;
+            const float wf = 0.65f * float(pieces) / float(nch), wb = 0.50f * float(pieces) / float(nblk_f);
+            int issued = 0;
+            uint32_t idle = 0;
+            char* zp = zb;
+            while (issued < pieces) {
+                const int fwd = ld_volatile_sa(landed_sa), bt = ld_volatile_sa(sm_sa + 2048 + 192);
+                int target = (p.dbg & 16) ? pieces : int(wf * float(fwd) + wb * float(bt)) + 2;
+                if (target > pieces) target = pieces;
+                if (issued < target) {
+                    for (; issued < target; ++issued) {
+                        const uint32_t bytes = uint32_t(min(size_t(kZeroPage), size_t(ze - zp)));
+                        bulk_s2g(zp, zero_sa, bytes);
+                        zp += bytes;
+                    }
+                    bulk_commit();
+                } else {
+                    __nanosleep(200);
+                    if (++idle > (1u << 24)) __trap();
+                }
+            }
+            bulk_wait_all();
+            fence_proxy_async();
+            __threadfence_block();
+            st_release_sa(sm_sa + 2048 + 196, 1);         // fill_done
+        }
+        return;
     }
 
     // bits (shared or global) and the zero-filled outputs become visible to the whole slot
@@ -600,28 +623,45 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     // idle logits ring; strip warp 0 runs the dependent chain on them.  Flags are plain shared counters again.
     const int kRmBlocks = (p.dbg & 32) ? 64 : 16;
     const unsigned conv_sleep = (p.dbg & 64) ? 1000u : 40u;
-    const int nconv = 2 * ns;                                   // strips 1.., the loaders, the filler
+    const int nconv = 2 * ns - 1;                               // strips 1.. and the loaders (the filler is still filling)
     const int nw = (m + 31) >> 5;                               // words per row
     const int nwp = nw | 1;                                     // odd pitch: the 32 rows of a block hit 32 banks
     const int nblk = (n + 31) >> 5;
     const uint32_t rm_sa = ring_sa;
     const uint32_t conv_sa = sm_sa + 2048 + 128;                // [nconv] blocks converted by converter h (it owns blocks k = h mod nconv)
     const uint32_t btdone_sa = sm_sa + 2048 + 192;              // blocks the chain has consumed
+    const uint32_t filldone_sa = sm_sa + 2048 + 196;            // set by the filler once every zero has landed
 
     if (!(role == 0 && s == 0)) {
         // ------------------------------- converter warp -----------------------------------
-        const int h = role == 0 ? s - 1 : (role == 1 ? ns - 1 + s : 2 * ns - 1);
+        const int h = role == 0 ? s - 1 : ns - 1 + s;
+        // Bits in the workspace come in through shared memory: the <= 9 word-rows a block of 32 rows touches are one bulk
+        // copy, double-buffered per converter behind the row-major ring (an L2 round trip per word would starve the chain).
+        constexpr int kStgRows = 9;
+        const uint32_t stgB = uint32_t(kStgRows) * uint32_t(wpt) * 4u;
+        const uint32_t cstg_sa = rm_sa + ((uint32_t(kRmBlocks * 32 * nwp) * 4u + 127u) & ~127u) + uint32_t(2 * h) * stgB;
+        const uint32_t cbar_sa = sm_sa + 640 + uint32_t(2 * h) * 8u;
+        const int nct = 2 * ((p.T1max + 31 + kR - 1) / kR) + 1;                 // word-rows per utterance in the workspace
+        auto stage_block = [&](int kb, int u) {
+            if (lane == 0) {
+                const int rlo = max(n - 1 - 32 * kb - 31, 0);
+                const int cb = rlo >> 3;
+                const uint32_t bytes = uint32_t(min(kStgRows, nct - cb)) * uint32_t(wpt) * 4u;
+                mbar_expect_tx_sa(cbar_sa + uint32_t(u) * 8u, bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(cstg_sa + uint32_t(u) * stgB), "l"(bits_g + size_t(cb) * wpt), "r"(bytes), "r"(cbar_sa + uint32_t(u) * 8u)
+                             : "memory");
+            }
+        };
         // The 32 backpointer bits of columns [32 qq, 32 qq + 32) of row `row`: global lane L = 8 qq + i holds row `row` in
         // the word of 8-step chunk (row + l) >> 3 (l = L mod 32) at nibble (row + l) & 7  ->  for i = 0..7 the nibble index
-        // runs cyclically from a = row & 7 and the chunk steps once, where a + i reaches 8.
-        auto bits_word = [&](int row, int qq) -> uint32_t {
+        // runs cyclically from a = row & 7 and the chunk steps once, where a + i reaches 8.  `base`: address of word-row 0.
+        auto bits_word = [&](uint32_t base, int row, int qq) -> uint32_t {
             const int a = row & 7;
             const int c0 = (row >> 3) + (qq & 3);
-            const uint32_t woff = uint32_t(c0) * uint32_t(wpt) + uint32_t(qq) * 8u;
-            const uint4 A0 = load_bits4<BITS_SMEM>(bits_g + woff, bits_sa + woff * 4u);
-            const uint4 A1 = load_bits4<BITS_SMEM>(bits_g + woff + 4, bits_sa + woff * 4u + 16u);
-            const uint4 B0 = load_bits4<BITS_SMEM>(bits_g + woff + wpt, bits_sa + (woff + wpt) * 4u);
-            const uint4 B1 = load_bits4<BITS_SMEM>(bits_g + woff + wpt + 4, bits_sa + (woff + wpt) * 4u + 16u);
+            const uint32_t wa = base + (uint32_t(c0) * uint32_t(wpt) + uint32_t(qq) * 8u) * 4u;
+            const uint4 A0 = lds_v4(wa), A1 = lds_v4(wa + 16u);
+            const uint4 B0 = lds_v4(wa + uint32_t(wpt) * 4u), B1 = lds_v4(wa + uint32_t(wpt) * 4u + 16u);
             const uint32_t A[8] = {A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w};
             const uint32_t Bv[8] = {B0.x, B0.y, B0.z, B0.w, B1.x, B1.y, B1.z, B1.w};
             const int sh = 4 * a;
@@ -634,8 +674,21 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             }
             return out;
         };
-        int done = 0, freed = 0;
+        int done = 0, freed = 0, u = 0;
+        uint32_t ph[2] = {0u, 0u};
+        if (!BITS_SMEM) {
+            fence_proxy_async();                                  // the ring was read and written through the generic proxy
+            if (h < nblk) stage_block(h, 0);
+        }
         for (int k = h; k < nblk; k += nconv) {
+            uint32_t base = bits_sa;
+            if (!BITS_SMEM) {
+                if (k + nconv < nblk) stage_block(k + nconv, u ^ 1);
+                mbar_wait_sa(cbar_sa + uint32_t(u) * 8u, ph[u]);
+                ph[u] ^= 1u;
+                base = cstg_sa + uint32_t(u) * stgB - uint32_t(max(n - 1 - 32 * k - 31, 0) >> 3) * uint32_t(wpt) * 4u;
+                u ^= 1;
+            }
             const int need = k - kRmBlocks + 1;                   // the ring slot's previous block must have been consumed
             uint32_t spins = 0;
             while (freed < need) {
@@ -644,7 +697,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             }
             const int row = n - 1 - 32 * k - lane;
             const uint32_t dst = rm_sa + uint32_t(((k & (kRmBlocks - 1)) * 32 + lane) * nwp) * 4u;
-            for (int qq = 0; qq < nw; ++qq) sts_u32(dst + uint32_t(qq) * 4u, row >= 1 ? bits_word(row, qq) : 0u);   // row 0 has no predecessor
+            for (int qq = 0; qq < nw; ++qq) sts_u32(dst + uint32_t(qq) * 4u, row >= 1 ? bits_word(base, row, qq) : 0u);   // row 0 has no predecessor
             __syncwarp();
             ++done;
             if (lane == 0) st_release_sa(conv_sa + 4u * h, done);
@@ -655,6 +708,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     // ----------------------------------- chain warp (strip warp 0) -------------------------
     int16_t* hard_b = p.hard + size_t(b) * p.T1max * p.T2max;
     int64_t* dur_b = p.dur ? p.dur + size_t(b) * p.T2max : nullptr;
+    int16_t* path_b = p.path_ws + size_t(b) * p.T1max;
     long long pc_conv = 0;
     auto wait_conv = [&](int h, int need, int seen) {            // warp-uniform: converter h has finished `need` blocks
         if (__any_sync(0xffffffffu, seen < need)) {
@@ -678,7 +732,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
         const int col = bj - __clz(bmyR);
         const uint32_t dec = __ballot_sync(0xffffffffu, (bmyR & bwin) != 0u);   // bit t: path leaves row bi0-t diagonally
         const bool valid = row >= 0;
-        stg_u16_if(hard_b + size_t(valid ? row : 0) * p.T2max + col, 1, valid && want_hard);
+        stg_u16_if(path_b + (valid ? row : 0), col, valid);                     // the 1 itself waits for the zero-fill
         // a token starts on this row if the path leaves it diagonally, or on row 0
         const bool starts = valid && (((dec >> lane) & 1u) || row == 0);
         const uint32_t smask = __ballot_sync(0xffffffffu, starts);
@@ -703,7 +757,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     int f_early = ld_volatile_sa(conv_sa + 4u * uint32_t(h1));
     const uint32_t win_sa = smem_u32(winbuf);
     int k = 0;
-    int pi0 = 0, pj = 0;                                      // the previous block, whose outputs are still to be written
+    int pi0 = -1, pj = 0;                                     // the previous block, whose outputs are still to be written
     uint32_t pmyR = 0x80000000u, pwin = 0;
     long long pc_pre = 0, pc_chain = 0, pc_epi = 0;
     for (int i0 = n - 1; i0 >= 0; i0 -= 32, ++k) {
@@ -734,7 +788,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             if (++h2 == nconv) { h2 = 0; ++need2; }
         }
         qw_pref = qw;
-        if (k > 0) emit(pi0, pj, pmyR, pwin, k - 1);
+        emit(pi0, pj, pmyR, pwin, k - 1);                       // (no branch: the first call has no valid row and writes nothing)
         uint32_t myR = 0x80000000u;
         uint32_t R = 0x80000000u;    // one-hot position inside the window; bit 31 <-> column j
 #pragma unroll
@@ -750,6 +804,22 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
         j -= __clz(R);                                          // R: position after the block's 32 rows (rows < 1 do not move it)
     }
     emit(pi0, pj, pmyR, pwin, k - 1);
+    if (probe) p.probe[14] = clock64();
+    // the ones: after the last zero has landed
+    {
+        uint32_t spins = 0;
+        while (ld_acquire_sa(filldone_sa) == 0) { __nanosleep(100); if (++spins > (1u << 24)) __trap(); }
+    }
+    __syncwarp();
+    if (want_hard) {
+        for (int r0 = 0; r0 < n; r0 += 256) {
+            int cols[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int r = r0 + 32 * i + lane; cols[i] = r < n ? int(__ldcg(path_b + r)) : 0; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int r = r0 + 32 * i + lane; if (r < n) hard_b[size_t(r) * p.T2max + cols[i]] = 1; }
+        }
+    }
     if (probe) { p.probe[3] = clock64(); p.probe[10] = pc_conv; p.probe[11] = pc_pre; p.probe[12] = pc_chain; p.probe[13] = pc_epi; }
 }
 
@@ -878,7 +948,7 @@ static bool make_maps(MasMaps* maps, const float* logp, int64_t sB, int64_t sT1,
 size_t mas_workspace_bytes(int B, int T1max, int T2max) {
     if (B <= 0 || T1max <= 0 || T2max <= 0) return 0;
     const int ns = (T2max + kW - 1) / kW;
-    return 256 + size_t(B) * bits_words_for(T1max, ns) * 4;
+    return 256 + size_t(B) * bits_words_for(T1max, ns) * 4 + ((size_t(B) * T1max * 2 + 15) & ~size_t(15));
 }
 
 template <bool BS, bool MULTI>
@@ -922,6 +992,7 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
     p.probe = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 64);
     p.bits_ws = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 256);
     p.bits_stride = int64_t(pl.bits_words);
+    p.path_ws = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(ws) + 256 + size_t(B) * pl.bits_words * 4);
     p.ns = pl.ns; p.slots = pl.slots; p.nstg = pl.nstg; p.wlast = pl.wlast;
     p.slot_bytes = int(pl.slot_bytes); p.dbg = g_opt_dbg;
     MasMaps maps;
