@@ -37,7 +37,10 @@
 namespace isp {
 
 constexpr int kTileM = 128;
-constexpr int kStagePitch = 36;                 // words per staged row: 16 B aligned, conflict-free
+constexpr int kCW = 16;                         // columns per epilogue chunk (one tcgen05.ld.x16)
+constexpr int kStagePitch = 20;                 // words per staged row: 16 B aligned, 5 x 16 B: conflict-free 128-bit stores
+constexpr int kEpiWarps = 8;                    // two per TMEM lane quadrant
+constexpr int kThreads = 32 * (1 + kEpiWarps);
 constexpr int kMaxSlabs = 8;                    // 128 B-wide K-slabs (D * elem <= 1024 B)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -143,6 +146,31 @@ ISP_DEVINL void tmem_st32(uint32_t taddr, const float (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+ISP_DEVINL void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
+ISP_DEVINL void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 ISP_DEVINL float fast_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -154,31 +182,32 @@ ISP_DEVINL float fast_lg2(float x) {
     return y;
 }
 
-// ---- staged, coalesced store of one 32-row x 32-column chunk -------------------------
+// ---- staged, coalesced store of one 32-row x 16-column chunk -------------------------
 // `stage` holds the warp's 32 rows (row = lane that produced it), kStagePitch words apart.
 ISP_DEVINL void store_chunk(const float* stage, float* gbase, int lane, int row0, int rows_valid,
                             int j0, int T2max, bool vec4) {
     // gbase points at element (b, 0, 0); row0 is the global frame index of staged row 0
     if (vec4) {
-        const int c4 = (lane & 7) * 4;
+        const int c4 = (lane & 3) * 4;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int rr = (lane >> 3) + 4 * it;
+        for (int it = 0; it < 4; ++it) {
+            const int rr = (lane >> 2) + 8 * it;
             if (rr < rows_valid && j0 + c4 < T2max) {
                 const float4 t = *reinterpret_cast<const float4*>(stage + rr * kStagePitch + c4);
                 *reinterpret_cast<float4*>(gbase + size_t(row0 + rr) * T2max + j0 + c4) = t;
             }
         }
     } else {
-        const bool colok = j0 + lane < T2max;
-        for (int rr = 0; rr < rows_valid; ++rr) {
-            if (colok) gbase[size_t(row0 + rr) * T2max + j0 + lane] = stage[rr * kStagePitch + lane];
+        const int cc = lane & 15;
+        const bool colok = j0 + cc < T2max;
+        for (int rr = lane >> 4; rr < rows_valid; rr += 2) {
+            if (colok) gbase[size_t(row0 + rr) * T2max + j0 + cc] = stage[rr * kStagePitch + cc];
         }
     }
 }
 
 template <bool TF32>
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(kThreads, 2)
 loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const LoglikParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -193,9 +222,10 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     // the 128 B swizzle atoms need 1024 B alignment; the launch adds 1 KB of slack for this
     unsigned char* smem_a = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* smem_b = smem_a + size_t(p.kslabs) * a_slab_bytes;
-    float* stage_all = reinterpret_cast<float*>(smem_b + size_t(p.kslabs) * b_slab_bytes);
-    float* gt = stage_all + 4 * 32 * kStagePitch;                       // [npad] j / T2_b
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gt + ((p.npad + 31) & ~31));
+    float* stage_all = reinterpret_cast<float*>(smem_b + size_t(p.kslabs) * b_slab_bytes);   // [8 warps][32][kStagePitch]
+    float* gt = stage_all + kEpiWarps * 32 * kStagePitch;               // [npad] j / T2_b
+    float4* xch = reinterpret_cast<float4*>(gt + ((p.npad + 31) & ~31)); // [2 halves][128 rows]: partial row statistics
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * kTileM);
     uint64_t* slab_full = bars;                                         // [kMaxSlabs]
     uint64_t* mma_done = bars + kMaxSlabs;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kMaxSlabs + 1);
@@ -251,8 +281,13 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             umma_commit(mma_done);
         }
     } else {
-        // ============================ epilogue: one thread per frame ====================
+        // ============================ epilogue: two threads per frame ===================
+        // Warps w and w + 4 share a TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ..) and split the
+        // row's 16-column chunks between them: even chunks to the first "half", odd ones to the second.  Row statistics
+        // are combined through shared memory, twice per tile.  Eight epilogue warps per CTA, sixteen per SM: the epilogue
+        // is a chain of MUFU and TMEM latencies, and only more warps hide it.
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may touch
+        const int half = (warp - 1) >> 2;                // 0: chunks 0, 2, 4, ...   1: chunks 1, 3, 5, ...
         const int r_in_tile = quad * 32 + lane;
         const int i = row_tile0 + r_in_tile;             // frame index
         const int warp_row0 = row_tile0 + quad * 32;
@@ -262,69 +297,69 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         float* g_logits = p.logits + size_t(b) * p.T1max * p.T2max;
         float* g_soft = p.soft + size_t(b) * p.T1max * p.T2max;
         const bool vec4 = p.vec4 != 0;
-        const int nchunks_all = (p.T2max + 31) >> 5;
+        const int nchunks_all = (p.T2max + kCW - 1) / kCW;
 
         if (all_padding) {
             // S == 0 on the whole tile: lse = log(T2max); attn_logits = -lse + log(1e-6); attn_soft = 0
             const float cst = kLogPriorFloor - logf(float(p.T2max));
-            for (int ch = 0; ch < nchunks_all; ++ch) {
+            for (int ch = half; ch < nchunks_all; ch += 2) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) my_stage[k] = p.prior ? cst : 0.0f;
+                for (int k = 0; k < kCW; ++k) my_stage[k] = p.prior ? cst : 0.0f;
                 __syncwarp();
-                store_chunk(stage, g_logits, lane, warp_row0, rows_valid, ch * 32, p.T2max, vec4);
+                store_chunk(stage, g_logits, lane, warp_row0, rows_valid, ch * kCW, p.T2max, vec4);
                 __syncwarp();
 #pragma unroll
-                for (int k = 0; k < 32; ++k) my_stage[k] = 0.0f;
+                for (int k = 0; k < kCW; ++k) my_stage[k] = 0.0f;
                 __syncwarp();
-                store_chunk(stage, g_soft, lane, warp_row0, rows_valid, ch * 32, p.T2max, vec4);
+                store_chunk(stage, g_soft, lane, warp_row0, rows_valid, ch * kCW, p.T2max, vec4);
                 __syncwarp();
             }
         } else {
             // j / T2_b exactly as the reference divides (alignment.py:22), once per CTA
             const float t2f = float(T2b);
-            for (int j = threadIdx.x - 32; j < p.npad; j += 128) gt[j] = __fdiv_rn(float(j), t2f);
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+            for (int j = threadIdx.x - 32; j < p.npad; j += 32 * kEpiWarps) gt[j] = __fdiv_rn(float(j), t2f);
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
 
             const bool row_valid = i < T1b;
             const float u = __fdiv_rn(float(i), float(T1b));   // alignment.py:25
             const float c = p.scale * kLog2e;
             const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
-            const int nchunks = (nb + 31) >> 5;               // chunks that hold MMA output
+            const int nchunks = nb / kCW;                      // chunks that hold MMA output (nb is a multiple of 16)
 
             mbar_wait(mma_done, 0);
             tc_fence_after();
 
-            float v[32];
+            float v[kCW];
             if (p.debug_scores) {
-                for (int ch = 0; ch < nchunks_all; ++ch) {
-                    if (ch < nchunks) tmem_ld32(tlane + ch * 32, v);
+                for (int ch = half; ch < nchunks_all; ch += 2) {
+                    if (ch < nchunks) tmem_ld16(tlane + ch * kCW, v);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) my_stage[k] = (ch < nchunks && ch * 32 + k < nb) ? v[k] * p.scale : 0.0f;
+                    for (int k = 0; k < kCW; ++k) my_stage[k] = (ch < nchunks && ch * kCW + k < nb) ? v[k] * p.scale : 0.0f;
                     __syncwarp();
-                    store_chunk(stage, g_logits, lane, warp_row0, rows_valid, ch * 32, p.T2max, vec4);
+                    store_chunk(stage, g_logits, lane, warp_row0, rows_valid, ch * kCW, p.T2max, vec4);
                     __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) my_stage[k] = 0.0f;
+                    for (int k = 0; k < kCW; ++k) my_stage[k] = 0.0f;
                     __syncwarp();
-                    store_chunk(stage, g_soft, lane, warp_row0, rows_valid, ch * 32, p.T2max, vec4);
+                    store_chunk(stage, g_soft, lane, warp_row0, rows_valid, ch * kCW, p.T2max, vec4);
                     __syncwarp();
                 }
             } else {
-                // ---- pass 1: online max / sum of exp over the valid columns; prior row sum ------
+                // ---- pass 1: online max / sum of exp over this half's valid columns; prior row sum ------
                 float m = -CUDART_INF_F, sum_e = 0.0f, psum = 0.0f;
-                for (int ch = 0; ch < nchunks; ++ch) {
-                    const int j0 = ch * 32;
-                    const int kmax = min(32, T2b - j0);
+                for (int ch = half; ch < nchunks; ch += 2) {
+                    const int j0 = ch * kCW;
+                    const int kmax = min(kCW, T2b - j0);
                     if (kmax <= 0) break;
-                    tmem_ld32(tlane + j0, v);
+                    tmem_ld16(tlane + j0, v);
                     float cm = -CUDART_INF_F;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) cm = fmaxf(cm, k < kmax ? v[k] : -CUDART_INF_F);
+                    for (int k = 0; k < kCW; ++k) cm = fmaxf(cm, k < kmax ? v[k] : -CUDART_INF_F);
                     const float mn = fmaxf(m, cm);
                     const float mnc = mn * c;
                     float acc = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
+                    for (int k = 0; k < kCW; ++k) {
                         const float e = fast_ex2(fmaf(v[k], c, -mnc));
                         acc += k < kmax ? e : 0.0f;
                     }
@@ -337,7 +372,7 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                         if (__any_sync(0xffffffffu, near)) {
                             float pacc = 0.0f;
 #pragma unroll
-                            for (int k4 = 0; k4 < 8; ++k4) {
+                            for (int k4 = 0; k4 < kCW / 4; ++k4) {
                                 const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
                                 const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
 #pragma unroll
@@ -349,6 +384,19 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                             psum += row_valid ? pacc : 0.0f;
                         }
                     }
+                }
+                // combine the two halves' statistics
+                xch[half * kTileM + r_in_tile] = make_float4(m, sum_e, psum, 0.0f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {
+                    const float4 o = xch[(half ^ 1) * kTileM + r_in_tile];
+                    const float mn = fmaxf(m, o.x);
+                    // a half with no valid chunk reports m = -inf, sum 0: its factor must not become NaN
+                    const float f0 = m == -CUDART_INF_F ? 0.0f : fast_ex2((m - mn) * c);
+                    const float f1 = o.x == -CUDART_INF_F ? 0.0f : fast_ex2((o.x - mn) * c);
+                    sum_e = sum_e * f0 + o.y * f1;
+                    psum = half == 0 ? psum + o.z : o.z + psum;       // the same order of addition in both halves
+                    m = mn;
                 }
                 if (T2b < p.T2max) {
                     // padded text columns have S == 0 exactly: add them in closed form
@@ -367,18 +415,18 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
                 // ---- pass 2: attn_logits, and w = exp(S - m) * (p + 1e-6) stashed in TMEM -------
                 float sum_w = 0.0f;
-                for (int ch = 0; ch < nchunks_all; ++ch) {
-                    const int j0 = ch * 32;
-                    const int kmax = min(32, T2b - j0);                        // valid text columns here
+                for (int ch = half; ch < nchunks_all; ch += 2) {
+                    const int j0 = ch * kCW;
+                    const int kmax = min(kCW, T2b - j0);                       // valid text columns here
                     if (ch < nchunks) {
-                        tmem_ld32(tlane + j0, v);
+                        tmem_ld16(tlane + j0, v);
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) v[k] = 0.0f;              // beyond the MMA extent: S == 0
+                        for (int k = 0; k < kCW; ++k) v[k] = 0.0f;             // beyond the MMA extent: S == 0
                     }
                     if (!p.prior) {
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
+                        for (int k = 0; k < kCW; ++k) {
                             my_stage[k] = v[k] * p.scale;
                             const float e = fast_ex2(fmaf(v[k], c, -mc));
                             v[k] = (k < kmax && row_valid) ? e : 0.0f;
@@ -392,7 +440,7 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                         }
                         if (__any_sync(0xffffffffu, near)) {
 #pragma unroll
-                            for (int k4 = 0; k4 < 8; ++k4) {
+                            for (int k4 = 0; k4 < kCW / 4; ++k4) {
                                 const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
                                 const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
 #pragma unroll
@@ -411,7 +459,7 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                             }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) {
+                            for (int k = 0; k < kCW; ++k) {
                                 my_stage[k] = fmaf(v[k], p.scale, -lse) + kLogPriorFloor;
                                 const float e = fast_ex2(fmaf(v[k], c, -mc));
                                 v[k] = (k < kmax && row_valid) ? e * kPriorEps : 0.0f;
@@ -419,27 +467,34 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                             }
                         }
                     }
-                    if (ch < nchunks && kmax > 0) tmem_st32(tlane + j0, v);
+                    if (ch < nchunks && kmax > 0) tmem_st16(tlane + j0, v);
                     __syncwarp();
                     store_chunk(stage, g_logits, lane, warp_row0, rows_valid, j0, p.T2max, vec4);
                     __syncwarp();
                 }
 
                 // ---- pass 3: attn_soft = w / sum(w) on valid cells, 0 elsewhere -----------------
+                asm volatile("bar.sync 1, 256;" ::: "memory");              // every thread has read the pass-1 statistics
+                xch[half * kTileM + r_in_tile].w = sum_w;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {
+                    const float o = xch[(half ^ 1) * kTileM + r_in_tile].w;
+                    sum_w = half == 0 ? sum_w + o : o + sum_w;
+                }
                 const float inv_w = row_valid ? 1.0f / sum_w : 0.0f;
                 tc_fence_before();
                 __syncwarp();
                 tc_fence_after();
-                for (int ch = 0; ch < nchunks_all; ++ch) {
-                    const int j0 = ch * 32;
-                    const int kmax = min(32, T2b - j0);
+                for (int ch = half; ch < nchunks_all; ch += 2) {
+                    const int j0 = ch * kCW;
+                    const int kmax = min(kCW, T2b - j0);
                     if (ch < nchunks && kmax > 0) {
-                        tmem_ld32(tlane + j0, v);
+                        tmem_ld16(tlane + j0, v);
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) my_stage[k] = k < kmax ? v[k] * inv_w : 0.0f;
+                        for (int k = 0; k < kCW; ++k) my_stage[k] = k < kmax ? v[k] * inv_w : 0.0f;
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) my_stage[k] = 0.0f;
+                        for (int k = 0; k < kCW; ++k) my_stage[k] = 0.0f;
                     }
                     __syncwarp();
                     store_chunk(stage, g_soft, lane, warp_row0, rows_valid, j0, p.T2max, vec4);
@@ -538,7 +593,7 @@ int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_
     if (rc) return rc;
 
     const size_t smem = size_t(p.kslabs) * (kTileM * 128 + size_t(p.nt) * p.boxrows_b * 128)
-                      + sizeof(float) * (4 * 32 * kStagePitch + ((p.npad + 31) & ~31))
+                      + sizeof(float) * (kEpiWarps * 32 * kStagePitch + ((p.npad + 31) & ~31) + 4 * 2 * kTileM)
                       + sizeof(uint64_t) * (kMaxSlabs + 2) + 1024 /* base alignment slack */;
     if (smem > 227 * 1024) { set_error("isp_loglik_forward: needs %zu B of shared memory (T2max=%d, D=%d)", smem, T2max, D); return ISP_ERR_UNSUPPORTED; }
 
@@ -547,11 +602,11 @@ int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_
     if (dtype == ISP_DTYPE_F32) {
         e = cudaFuncSetAttribute(loglik_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(loglik_kernel<tf32>)");
-        loglik_kernel<true><<<grid, 160, smem, stream>>>(mq, mk, p);
+        loglik_kernel<true><<<grid, kThreads, smem, stream>>>(mq, mk, p);
     } else {
         e = cudaFuncSetAttribute(loglik_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(loglik_kernel<bf16>)");
-        loglik_kernel<false><<<grid, 160, smem, stream>>>(mq, mk, p);
+        loglik_kernel<false><<<grid, kThreads, smem, stream>>>(mq, mk, p);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "loglik_kernel launch");
