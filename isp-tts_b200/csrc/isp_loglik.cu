@@ -248,6 +248,28 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = all_padding ? 0u : *tmem_slot;
 
+    if (all_padding) {
+        // S == 0 on the whole tile: lse = log(T2max); attn_logits = -lse + log(1e-6); attn_soft = 0.  The tile's rows are
+        // one contiguous block of each output: a straight coalesced fill by every thread of the CTA.
+        const float cst = p.prior ? kLogPriorFloor - logf(float(p.T2max)) : 0.0f;
+        const int rows = min(kTileM, p.T1max - row_tile0);
+        const size_t off = (size_t(b) * p.T1max + row_tile0) * p.T2max;
+        const size_t nelem = size_t(rows) * p.T2max;
+        float* gl = p.logits + off;
+        float* gs = p.soft + off;
+        if (p.vec4) {
+            const float4 c4 = make_float4(cst, cst, cst, cst), z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const size_t n4 = nelem >> 2;
+            for (size_t idx = threadIdx.x; idx < n4; idx += kThreads) {
+                __stcs(reinterpret_cast<float4*>(gl) + idx, c4);
+                __stcs(reinterpret_cast<float4*>(gs) + idx, z4);
+            }
+        } else {
+            for (size_t idx = threadIdx.x; idx < nelem; idx += kThreads) { gl[idx] = cst; gs[idx] = 0.0f; }
+        }
+        return;
+    }
+
     if (warp == 0) {
         // ============================ TMA + MMA issue ===================================
         if (!all_padding && lane == 0) {
@@ -352,16 +374,27 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     const int kmax = min(kCW, T2b - j0);
                     if (kmax <= 0) break;
                     tmem_ld16(tlane + j0, v);
+                    const bool full = kmax == kCW;              // warp-uniform: no column masks in the common case
                     float cm = -CUDART_INF_F;
+                    if (full) {
 #pragma unroll
-                    for (int k = 0; k < kCW; ++k) cm = fmaxf(cm, k < kmax ? v[k] : -CUDART_INF_F);
+                        for (int k = 0; k < kCW; ++k) cm = fmaxf(cm, v[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kCW; ++k) cm = fmaxf(cm, k < kmax ? v[k] : -CUDART_INF_F);
+                    }
                     const float mn = fmaxf(m, cm);
                     const float mnc = mn * c;
                     float acc = 0.0f;
+                    if (full) {
 #pragma unroll
-                    for (int k = 0; k < kCW; ++k) {
-                        const float e = fast_ex2(fmaf(v[k], c, -mnc));
-                        acc += k < kmax ? e : 0.0f;
+                        for (int k = 0; k < kCW; ++k) acc += fast_ex2(fmaf(v[k], c, -mnc));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kCW; ++k) {
+                            const float e = fast_ex2(fmaf(v[k], c, -mnc));
+                            acc += k < kmax ? e : 0.0f;
+                        }
                     }
                     sum_e = sum_e * fast_ex2((m - mn) * c) + acc;
                     m = mn;
@@ -378,7 +411,7 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const float p0 = fast_ex2(gg[q] * gg[q] * (kNegInvTwoGammaSq * kLog2e));
-                                    pacc += (4 * k4 + q) < kmax ? p0 : 0.0f;
+                                    pacc += (full || (4 * k4 + q) < kmax) ? p0 : 0.0f;
                                 }
                             }
                             psum += row_valid ? pacc : 0.0f;
@@ -418,6 +451,16 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 for (int ch = half; ch < nchunks_all; ch += 2) {
                     const int j0 = ch * kCW;
                     const int kmax = min(kCW, T2b - j0);                       // valid text columns here
+                    if (kmax <= 0) {
+                        // padded text columns only: S == 0, so attn_logits is one constant per row and w is 0
+                        const float cst = p.prior ? kLogPriorFloor - lse : 0.0f;
+#pragma unroll
+                        for (int k = 0; k < kCW; ++k) my_stage[k] = cst;
+                        __syncwarp();
+                        store_chunk(stage, g_logits, lane, warp_row0, rows_valid, j0, p.T2max, vec4);
+                        __syncwarp();
+                        continue;
+                    }
                     if (ch < nchunks) {
                         tmem_ld16(tlane + j0, v);
                     } else {
@@ -438,24 +481,52 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                             const float glo = gt[j0] - u, ghi = gt[j0 + kmax - 1] - u;
                             near = glo <= gband && ghi >= -gband;
                         }
+                        // warp-uniform: every column of the chunk is a valid token and every row of the warp a valid frame
+                        const bool full = kmax == kCW && __all_sync(0xffffffffu, row_valid);
                         if (__any_sync(0xffffffffu, near)) {
+                            if (full) {
 #pragma unroll
-                            for (int k4 = 0; k4 < kCW / 4; ++k4) {
-                                const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
-                                const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
+                                for (int k4 = 0; k4 < kCW / 4; ++k4) {
+                                    const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
+                                    const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int k = 4 * k4 + q;
-                                    const bool ok = k < kmax && row_valid;
-                                    float pr = fast_ex2(gg[q] * gg[q] * (kNegInvTwoGammaSq * kLog2e)) * inv_psum;
-                                    pr = (ok && pr >= kPriorThreshold) ? pr : 0.0f;
-                                    const float P = pr + kPriorEps;
-                                    const float lp = fast_lg2(P) * kLn2;
-                                    my_stage[k] = fmaf(v[k], p.scale, -lse) + lp;
-                                    const float e = fast_ex2(fmaf(v[k], c, -mc));
-                                    v[k] = ok ? e * P : 0.0f;
-                                    sum_w += v[k];
+                                    for (int q = 0; q < 4; ++q) {
+                                        const int k = 4 * k4 + q;
+                                        float pr = fast_ex2(gg[q] * gg[q] * (kNegInvTwoGammaSq * kLog2e)) * inv_psum;
+                                        pr = pr >= kPriorThreshold ? pr : 0.0f;
+                                        const float P = pr + kPriorEps;
+                                        const float lp = fast_lg2(P) * kLn2;
+                                        my_stage[k] = fmaf(v[k], p.scale, -lse) + lp;
+                                        v[k] = fast_ex2(fmaf(v[k], c, -mc)) * P;
+                                        sum_w += v[k];
+                                    }
                                 }
+                            } else {
+#pragma unroll
+                                for (int k4 = 0; k4 < kCW / 4; ++k4) {
+                                    const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
+                                    const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const int k = 4 * k4 + q;
+                                        const bool ok = k < kmax && row_valid;
+                                        float pr = fast_ex2(gg[q] * gg[q] * (kNegInvTwoGammaSq * kLog2e)) * inv_psum;
+                                        pr = (ok && pr >= kPriorThreshold) ? pr : 0.0f;
+                                        const float P = pr + kPriorEps;
+                                        const float lp = fast_lg2(P) * kLn2;
+                                        my_stage[k] = fmaf(v[k], p.scale, -lse) + lp;
+                                        const float e = fast_ex2(fmaf(v[k], c, -mc));
+                                        v[k] = ok ? e * P : 0.0f;
+                                        sum_w += v[k];
+                                    }
+                                }
+                            }
+                        } else if (full) {
+#pragma unroll
+                            for (int k = 0; k < kCW; ++k) {
+                                my_stage[k] = fmaf(v[k], p.scale, -lse) + kLogPriorFloor;
+                                v[k] = fast_ex2(fmaf(v[k], c, -mc)) * kPriorEps;
+                                sum_w += v[k];
                             }
                         } else {
 #pragma unroll
@@ -490,8 +561,13 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     const int kmax = min(kCW, T2b - j0);
                     if (ch < nchunks && kmax > 0) {
                         tmem_ld16(tlane + j0, v);
+                        if (kmax == kCW) {
 #pragma unroll
-                        for (int k = 0; k < kCW; ++k) my_stage[k] = k < kmax ? v[k] * inv_w : 0.0f;
+                            for (int k = 0; k < kCW; ++k) my_stage[k] = v[k] * inv_w;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kCW; ++k) my_stage[k] = k < kmax ? v[k] * inv_w : 0.0f;
+                        }
                     } else {
 #pragma unroll
                         for (int k = 0; k < kCW; ++k) my_stage[k] = 0.0f;

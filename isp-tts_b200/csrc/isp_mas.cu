@@ -62,6 +62,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "isp_internal.h"
 
@@ -362,14 +364,14 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             lds_row(xc, lane_ring + rd);                               // the row of step 0
             rd += pitchB; if (rd >= ringB) rd -= ringB;
             int st_free = 0;                                           // stage of chunk ch - 3
-            int st_cur = 0;                                            // stage of chunk ch
             uint32_t bits_off = uint32_t(s * 32 + lane) * 4u;          // byte offset of this lane's first word of chunk ch
             int prog_seen = 0, cons_seen = 0, p_early = 0, c_early = 0;
 
             // All waits below are on plain shared counters, read one chunk (or half a chunk) before they are looked at:
             // an mbarrier test costs the warp ~100 cycles even when the phase is long complete, an acquire load ~70.
             // Branches on them are made warp-uniform with a vote, which keeps the common path free of divergence handling.
-            for (int ch = 0; ch < nch; ++ch) {
+            auto run_chunk = [&](const int ch, auto head_tag) __attribute__((always_inline)) {
+                constexpr bool HEAD = decltype(head_tag)::value;   // some lane starts its row 0 in this chunk (chunks 0 and 1)
                 const int t0 = ch * kR;
                 // ---- chunk top: free the stage whose last reader has moved on (chunk ch - 3) ----
                 __syncwarp();
@@ -461,22 +463,9 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
                         _Pragma("unroll") for (int c = 0; c < kC; ++c) xc[c] = xn[c];                              \
                     }
                     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    long long cl0 = 0;
-                    if (probe_w) cl0 = clock64();
-                    if (ch < 2) {
 #pragma unroll
-                        for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, true)
-                    } else if (st_cur >= 2 && st_cur + 1 < nstg) {
-                        // the lanes read rows t0 - 30 .. t0 + 16, i.e. stages st_cur - 2 .. st_cur + 1: no wrap
-#pragma unroll
-                        for (int k = 0; k < kR; ++k) ISP_MAS_STEP(false, false)
-                        if (rd >= ringB) rd -= ringB;                  // the chunk may end exactly on the ring's end
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, false)
-                    }
+                    for (int k = 0; k < kR; ++k) ISP_MAS_STEP(true, HEAD)
 #undef ISP_MAS_STEP
-                    if (probe_w) { pc_loop += clock64() - cl0; pc_nloop += 1; }
                     word0 = __byte_perm(__float_as_uint(acc[0] + 8388608.0f), __float_as_uint(acc[1] + 8388608.0f), 0x5410);
                     word1 = __byte_perm(__float_as_uint(acc[2] + 8388608.0f), __float_as_uint(acc[3] + 8388608.0f), 0x5410);
                 }
@@ -488,10 +477,13 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
                     bits_g[(bits_off >> 2) + wpt] = word1;
                 }
                 bits_off += uint32_t(wpt) * 8u;
-                st_cur = st_cur + 1 == nstg ? 0 : st_cur + 1;
                 // the publishing lane's 16 stores precede this one in program order; shared memory keeps a thread's stores in order
                 if (MULTI) st_volatile_if_sa(prog_sa + 4u * s, ch + 1, pub);
-            }
+            };
+            // One straight-line body per chunk: jumping between specialised variants of the 16 steps cost more in instruction
+            // fetch (a few far branches per chunk) than the two instructions per step that the ring-wrap check takes.
+            for (int ch = 0; ch < 2 && ch < nch; ++ch) run_chunk(ch, std::true_type{});
+            for (int ch = 2; ch < nch; ++ch) run_chunk(ch, std::false_type{});
         }
     } else if (role == 1) {
         // =========================== loader warp of strip s ================================
@@ -675,7 +667,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             return out;
         };
         int done = 0, freed = 0, u = 0;
-        uint32_t ph[2] = {0u, 0u};
+        uint32_t ph0 = 0u, ph1 = 0u;
         if (!BITS_SMEM) {
             fence_proxy_async();                                  // the ring was read and written through the generic proxy
             if (h < nblk) stage_block(h, 0);
@@ -684,8 +676,8 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             uint32_t base = bits_sa;
             if (!BITS_SMEM) {
                 if (k + nconv < nblk) stage_block(k + nconv, u ^ 1);
-                mbar_wait_sa(cbar_sa + uint32_t(u) * 8u, ph[u]);
-                ph[u] ^= 1u;
+                mbar_wait_sa(cbar_sa + uint32_t(u) * 8u, u ? ph1 : ph0);
+                if (u) ph1 ^= 1u; else ph0 ^= 1u;
                 base = cstg_sa + uint32_t(u) * stgB - uint32_t(max(n - 1 - 32 * k - 31, 0) >> 3) * uint32_t(wpt) * 4u;
                 u ^= 1;
             }
