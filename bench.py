@@ -117,13 +117,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_step(q, k, tl, ml, scale):
+def cpu_step(q, k, tl, ml, scale, nthreads=0):
     """One hot-path pass on the CPU: reference op sequence in torch-CPU + the C/OpenMP MAS."""
     import torch
     from oracle import loglik_torch as olt
     from oracle import mas as omas
     soft, logits = olt.loglik(q, k, tl, ml, scale)
-    hard, dur = omas.b_mas_with_durations(logits.numpy(), tl.numpy(), ml.numpy())
+    hard, dur = omas.b_mas_with_durations(logits.numpy(), tl.numpy(), ml.numpy(), nthreads)
     return dur
 
 
@@ -137,15 +137,18 @@ def cpu_baseline(w, sample_utts, reps, warm=1):
     q, k = synth.encoded_pair(n, w.t1max, w.t2max, w.dim, tl, ml, w.seed + 1)
     qt, kt, tlt, mlt = torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(tl), torch.from_numpy(ml)
     scale = w.dim ** -0.5
+    # every host core, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
     for _ in range(warm):
-        cpu_step(qt, kt, tlt, mlt, scale)
+        cpu_step(qt, kt, tlt, mlt, scale, ncores)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_step(qt, kt, tlt, mlt, scale)
+        cpu_step(qt, kt, tlt, mlt, scale, ncores)
         times.append(time.perf_counter() - t0)
     best = min(times)
-    cores = max(torch.get_num_threads(), omas.num_threads())
+    cores = ncores
     return {
         "value": n / best, "unit": UNIT, "cores": int(cores), "kind": "port",
         "sample": f"first {n} of {w.batch} utterances of {w.name}; fp32; best of {reps} "
