@@ -71,8 +71,9 @@ int         isp_device_check(void);
  * attn_hard (B, T1max, T2max) int16, contiguous, FULLY written: exactly one 1 per
  *           valid frame, 0 elsewhere (padding included) -- it need not be pre-zeroed.
  * durations (B, T2max) int64, contiguous, fully written; may be NULL.
- * ws        isp_mas_workspace_bytes(B,T1max,T2max) bytes, 16 B aligned; holds the packed
- *           backpointer bits when they do not fit in shared memory, and the status word.
+ * ws        isp_mas_workspace_bytes(B,T1max,T2max) bytes, 16 B aligned; holds the status word,
+ *           the packed backpointer bits when they do not fit in shared memory, and the
+ *           path's column per frame until the zero-fill of attn_hard has landed.
  * Limits:   T2max <= ISP_MAS_MAX_T2; T1max < 2^24.
  * Results are bit-identical to the reference for NaN-free input.
  */
@@ -112,8 +113,12 @@ int    isp_loglik_forward(const void* Q, const void* K, int dtype,
                           void* ws, size_t ws_bytes, void* stream);
 
 /* Tuning knobs for benchmarks/tests (process-wide, not part of the drop-in contract).
- *   "mas.cols_per_lane"  4 | 8 | 0 (= heuristic)
- *   "mas.ring_rows"      rows of logits kept in flight per utterance, 0 = heuristic
+ *   "mas.ring_rows"      rows of logits kept in flight per strip of 128 tokens, 0 = heuristic
+ *   "mas.slots"          utterances per CTA (1 | 2), 0 = heuristic
+ *   "mas.bits_global"    1: backpointer bits always in the workspace
+ *   "mas.no_tma"         1: 4 B async copies instead of tiled TMA boxes (the path taken when the
+ *                        logits are not 16 B aligned or T2max is not a multiple of 4)
+ *   "mas.dbg"            profiling switches, see isp_mas.cu
  * Returns the previous value, or ISP_ERR_INVALID for an unknown key. */
 int isp_set_option(const char* key, int value);
 
