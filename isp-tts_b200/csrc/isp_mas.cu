@@ -119,13 +119,14 @@ ISP_DEVINL int ld_volatile_sa(uint32_t saddr) {
     asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
     return v;
 }
-// predicated forms: a divergent `if (lane == ...)` around one instruction costs BSSY/BSYNC and a branch
+// predicated forms: a divergent `if (lane == ...)` around one instruction costs BSSY/BSYNC and a branch.  The counter
+// stores are plain st.shared inside `asm volatile` (the compiler keeps their place; st.volatile would add a MEMBAR)
 ISP_DEVINL void mbar_arrive_if_sa(uint32_t bar, bool pred) {
     asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 st;\n\tsetp.ne.u32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
                  ::"r"(bar), "r"(uint32_t(pred)) : "memory");
 }
 ISP_DEVINL void st_volatile_if_sa(uint32_t saddr, int v, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.volatile.shared::cta.s32 [%0], %1;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared::cta.s32 [%0], %1;\n\t}"
                  ::"r"(saddr), "r"(v), "r"(uint32_t(pred)) : "memory");
 }
 ISP_DEVINL void sts_f32_if(uint32_t saddr, float v, bool pred) {
@@ -142,7 +143,7 @@ ISP_DEVINL void sts_u64(uint32_t saddr, uint32_t lo, uint32_t hi) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(lo), "r"(hi) : "memory");
 }
 ISP_DEVINL void st_volatile_sa(uint32_t saddr, int v) {
-    asm volatile("st.volatile.shared::cta.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+    asm volatile("st.shared::cta.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 ISP_DEVINL void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
@@ -708,7 +709,9 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             uint32_t spins = 0;
             long long c0 = 0;
             if (probe_w) c0 = clock64();
-            while (ld_acquire_sa(fa) < need) { if (++spins > (1u << 26)) __trap(); }
+            // plain loads: the converter's words and its counter are stored in program order by one lane group and shared
+            // memory keeps that order; an acquire load would put a MEMBAR on the chain for every block
+            while (ld_volatile_sa(fa) < need) { if (++spins > (1u << 26)) __trap(); }
             if (probe_w) pc_conv += clock64() - c0;
         }
     };
