@@ -316,12 +316,44 @@ def run_ours(args, w):
     if int(dur_host.sum()) != int(ml.sum()):
         raise RuntimeError("durations do not sum to the mel lengths")
 
+    # ---- next row: backward of the log-likelihood, measured beside the hot path ----------
+    bwd = None
+    if rank == 0 and not args.no_backward:
+        from isp_tts_b200.alignment import _scores, loglik_backward_ds
+        soft_b, logits_b = _loglik_cuda(q_dev, k_dev, tl_dev, ml_dev, scale, True)
+        gen = torch.Generator(device=dev).manual_seed(1)
+        g_l = torch.randn(soft_b.shape, device=dev, generator=gen)
+        g_s = torch.randn(soft_b.shape, device=dev, generator=gen)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        t_s, t_ds, t_mm = [], [], []
+        for it in range(8):
+            ev[0].record()
+            sc = _scores(q_dev, k_dev)
+            ev[1].record()
+            d_s = loglik_backward_ds(sc, soft_b, g_l, g_s, scale, True, out_dtype=gemm_dtype)
+            ev[2].record()
+            gq = torch.matmul(d_s, k_dev)
+            gk = torch.matmul(d_s.transpose(1, 2), q_dev)
+            ev[3].record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                t_s.append(ev[0].elapsed_time(ev[1])); t_ds.append(ev[1].elapsed_time(ev[2])); t_mm.append(ev[2].elapsed_time(ev[3]))
+        by_ds = (16 + elem) * B * T1 * T2
+        bwd = {"row": "f-1 backward of the log-likelihood (d attn_logits, d attn_soft -> dQ, dK)",
+               "isp_loglik_backward_ds": {"ms": float(np.mean(t_ds)), "algorithmic_bytes": by_ds,
+                                          "gbs": by_ds / float(np.mean(t_ds)) / 1e6},
+               "library_gemms_ms": {"scores_QKt": float(np.mean(t_s)), "dQ_and_dK": float(np.mean(t_mm))},
+               "total_ms": float(np.mean(t_s) + np.mean(t_ds) + np.mean(t_mm))}
+        del soft_b, logits_b, g_l, g_s, sc, d_s, gq, gk
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     hbm_peak, tf_peak, which = load_peaks()
+    if bwd is not None:
+        bwd["isp_loglik_backward_ds"]["hbm_frac"] = bwd["isp_loglik_backward_ds"]["gbs"] / hbm_peak
     by_mas = mas_bytes(tl, ml, B, T1, T2)
     by_ll = loglik_bytes(B, T1, T2, D, elem)
     fl_ll = loglik_flops(B, T1, T2, D)
@@ -367,6 +399,7 @@ def run_ours(args, w):
                 "d2h_bytes_per_step": int(dur_host.numel() * 8), "ms_per_step": e2e_ms / args.steps,
                 "api": "isp_loglik_forward + isp_mas_forward through isp_tts_b200 (pinned host Q, K, lengths in; durations out); "
                        "the next step's H2D overlaps this step's kernels (two device buffers, one copy stream)"},
+        "next_rows": bwd,
         "gpu_launches": 2 * args.steps,
         "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
     }
@@ -385,6 +418,7 @@ def main():
     ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--mas-ring", type=int, default=0, help="tuning: MAS logit rows in flight, 0 = heuristic")
     ap.add_argument("--mas-slots", type=int, default=0, help="tuning: utterances per CTA (1|2), 0 = heuristic")
+    ap.add_argument("--no-backward", action="store_true", help="skip the f-1 backward measurement that follows the timed steps")
     args = ap.parse_args()
     from isp_tts_b200 import synth
     w = synth.WORKLOADS[args.workload]

@@ -112,6 +112,22 @@ int    isp_loglik_forward(const void* Q, const void* K, int dtype,
                           float* attn_logits, float* attn_soft,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward of the log-likelihood, first stage: the gradient with respect to the scores S = Q.K^T.
+ *
+ * Replaces what autograd records for tts/models/acoustic/modules/alignment.py:190-206 (scale,
+ * log_softmax over all T2max columns, + log prior, masked softmax): given
+ *   S          (B, T1max, T2max) fp32, the UNscaled scores Q.K^T (recomputed by a library GEMM)
+ *   attn_soft  (B, T1max, T2max) fp32, as returned by isp_loglik_forward
+ *   g_logits   dL/d attn_logits, g_soft  dL/d attn_soft  (either may be NULL, not both)
+ * it writes dS = dL/dS (fp32 or bf16, ds_dtype = ISP_DTYPE_*), from which dQ = dS.K and dK = dS^T.Q
+ * are plain batched GEMMs (cuBLAS).  All tensors contiguous and 16 B aligned; T2max % 4 == 0,
+ * T2max <= ISP_LOGLIK_MAX_T2.  One pass: every input is read once, dS is written once.
+ */
+int    isp_loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
+                              int B, int T1max, int T2max, float scale, int attention_prior,
+                              void* dS, int ds_dtype, void* stream);
+
 /* Tuning knobs for benchmarks/tests (process-wide, not part of the drop-in contract).
  *   "mas.ring_rows"      rows of logits kept in flight per strip of 128 tokens, 0 = heuristic
  *   "mas.slots"          utterances per CTA (1 | 2), 0 = heuristic

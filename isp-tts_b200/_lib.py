@@ -17,7 +17,7 @@ ISP_DTYPE_BF16 = 1
 EXPORTS = [
     "isp_version", "isp_last_error", "isp_device_check",
     "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_status",
-    "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_set_option",
+    "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_set_option",
 ]
 
 _lib = None
@@ -51,6 +51,8 @@ def load():
     lib.isp_loglik_workspace_bytes.restype = c_sz
     lib.isp_loglik_forward.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, f32, c_int, vp, vp, vp, c_sz, vp]
     lib.isp_loglik_forward.restype = c_int
+    lib.isp_loglik_backward_ds.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, f32, c_int, vp, c_int, vp]
+    lib.isp_loglik_backward_ds.restype = c_int
     lib.isp_set_option.argtypes = [ctypes.c_char_p, c_int]
     lib.isp_set_option.restype = c_int
     _lib = lib

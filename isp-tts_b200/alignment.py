@@ -179,35 +179,65 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
     return soft, logits
 
 
+def _scores(q: Tensor, k: Tensor) -> Tensor:
+    """Unscaled S = Q.K^T in fp32 (a plain library GEMM; bf16 operands keep an fp32 result)."""
+    if q.dtype == torch.float32:
+        return torch.matmul(q, k.transpose(1, 2))
+    try:
+        return torch.bmm(q, k.transpose(1, 2), out_dtype=torch.float32)
+    except TypeError:                                   # older torch: no out_dtype on bmm
+        return torch.matmul(q.float(), k.float().transpose(1, 2))
+
+
+def loglik_backward_ds(scores: Tensor, soft: Tensor, g_logits: Tensor | None, g_soft: Tensor | None, scale: float,
+                       prior: bool, out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """dL/dS from the incoming gradients: the sm_100a kernel behind isp_loglik_backward_ds
+    (alignment.py:190-206 differentiated; one pass over the four (B, T1, T2) inputs)."""
+    dev = scores.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    B, T1, T2 = scores.shape
+    pad = (-T2) % 4
+    def prep(t):
+        if t is None:
+            return None
+        t = t.float()
+        if pad:
+            t = torch.nn.functional.pad(t, (0, pad))    # the kernel wants 16 B rows; padded scores must not count
+        return t.contiguous()
+    s_, a_, gl_, gs_ = prep(scores), prep(soft), prep(g_logits), prep(g_soft)
+    if pad:
+        s_[:, :, T2:] = float("-inf")
+    ds = torch.empty((B, T1, T2 + pad), dtype=out_dtype, device=dev)
+    dt = _lib.ISP_DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+    with torch.cuda.device(dev):
+        rc = lib.isp_loglik_backward_ds(s_.data_ptr(), a_.data_ptr(), gl_.data_ptr() if gl_ is not None else None,
+                                        gs_.data_ptr() if gs_ is not None else None, B, T1, T2 + pad, float(scale),
+                                        1 if prior else 0, ds.data_ptr(), dt, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "isp_loglik_backward_ds")
+    return ds[:, :, :T2] if pad else ds
+
+
 class _LogLikelihood(torch.autograd.Function):
-    """forward: the fused sm_100a kernel.  backward: composed from torch ops for now
-    (the fused backward is SURVEY.md section 8 f-1)."""
+    """forward: the fused sm_100a kernel.  backward: the scores are recomputed by a library
+    GEMM, dS comes from the sm_100a kernel behind isp_loglik_backward_ds, dQ = dS.K and dK = dS^T.Q are library GEMMs."""
 
     @staticmethod
     def forward(ctx, q, k, text_len, mel_len, scale, prior):
         soft, logits = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior)
-        ctx.save_for_backward(q, k, text_len, mel_len, soft)
+        ctx.save_for_backward(q, k, soft)
         ctx.scale, ctx.prior = scale, prior
         return soft, logits
 
     @staticmethod
     def backward(ctx, g_soft, g_logits):
-        q, k, text_len, mel_len, soft = ctx.saved_tensors
-        qf, kf = q.float(), k.float()
-        g_total = torch.zeros_like(soft) if g_logits is None else g_logits.float().clone()
-        if g_soft is not None:
-            # attn_soft = softmax over valid text of attn_logits, times mask (alignment.py:201-206)
-            gs = g_soft.float()
-            g_total = g_total + soft * (gs - (gs * soft).sum(dim=2, keepdim=True))
-        if ctx.prior:
-            # attn_logits = S - logsumexp_all(S) + const (alignment.py:196)
-            s = ctx.scale * torch.matmul(qf, kf.transpose(1, 2))
-            d_s = g_total - torch.softmax(s, dim=2) * g_total.sum(dim=2, keepdim=True)
-        else:
-            d_s = g_total
-        d_s = d_s * ctx.scale
-        gq = torch.matmul(d_s, kf).to(q.dtype) if ctx.needs_input_grad[0] else None
-        gk = torch.matmul(d_s.transpose(1, 2), qf).to(k.dtype) if ctx.needs_input_grad[1] else None
+        q, k, soft = ctx.saved_tensors
+        if g_soft is None and g_logits is None:
+            return None, None, None, None, None, None
+        qd, kd = q.detach(), k.detach()
+        d_s = loglik_backward_ds(_scores(qd, kd), soft, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
+        gq = torch.matmul(d_s, kd) if ctx.needs_input_grad[0] else None
+        gk = torch.matmul(d_s.transpose(1, 2), qd) if ctx.needs_input_grad[1] else None
         return gq, gk, None, None, None, None
 
 

@@ -71,6 +71,12 @@ int isp_loglik_forward(const void* Q, const void* K, int dtype, const int64_t* t
                                attn_logits, attn_soft, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int isp_loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
+                           int B, int T1max, int T2max, float scale, int attention_prior, void* dS, int ds_dtype, void* stream) {
+    return isp::loglik_backward_ds(S, attn_soft, g_logits, g_soft, B, T1max, T2max, scale, attention_prior, dS, ds_dtype,
+                                   static_cast<cudaStream_t>(stream));
+}
+
 int isp_set_option(const char* key, int value) {
     if (!key) return ISP_ERR_INVALID;
     int prev = 0;

@@ -24,5 +24,7 @@ int    loglik_forward(const void* Q, const void* K, int dtype, const int64_t* te
                       int B, int T1max, int T2max, int D, float scale, int attention_prior,
                       float* attn_logits, float* attn_soft, void* ws, size_t ws_bytes, cudaStream_t stream);
 int    loglik_set_option(const char* key, int value, int* prev);
+int    loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
+                          int B, int T1max, int T2max, float scale, int attention_prior, void* dS, int ds_dtype, cudaStream_t stream);
 
 }  // namespace isp

@@ -148,3 +148,60 @@ def test_backward_matches_torch_autograd(cuda_device):
     (sf * w1).sum().add((lg * w2).sum()).backward()
     assert torch.allclose(gq, q2.grad, rtol=2e-3, atol=2e-3), (gq - q2.grad).abs().max()
     assert torch.allclose(gk, k2.grad, rtol=2e-3, atol=2e-3), (gk - k2.grad).abs().max()
+
+
+def _torch_ds(s, soft, gl, gs, scale, prior):
+    """dL/dS by the book (alignment.py:190-206 differentiated), fp64 on the GPU."""
+    s, soft = s.double(), soft.double()
+    g = torch.zeros_like(s) if gl is None else gl.double().clone()
+    if gs is not None:
+        g = g + soft * (gs.double() - (gs.double() * soft).sum(2, keepdim=True))
+    if prior:
+        g = g - torch.softmax(scale * s, dim=2) * g.sum(2, keepdim=True)
+    return g * scale
+
+
+@pytest.mark.parametrize("T2", [200, 24, 37, 512])
+@pytest.mark.parametrize("which", ["both", "logits", "soft"])
+def test_backward_ds_kernel(cuda_device, T2, which):
+    """isp_loglik_backward_ds against the closed-form Jacobians, incl. a token axis that needs padding (37)."""
+    from isp_tts_b200.alignment import loglik_backward_ds
+    B, T1, D = 3, 130, 64
+    tl, ml = synth.lengths(B, T2, T1, True, 7)
+    qn, kn = synth.encoded_pair(B, T1, T2, D, tl, ml, 8)
+    q, k = torch.from_numpy(qn).to(cuda_device), torch.from_numpy(kn).to(cuda_device)
+    tlt, mlt = torch.from_numpy(tl).to(cuda_device), torch.from_numpy(ml).to(cuda_device)
+    soft, logits = loglik_forward(q, k, tlt, mlt)
+    s = torch.matmul(q, k.transpose(1, 2))
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    gl = torch.randn(soft.shape, device=cuda_device, generator=gen) if which != "soft" else None
+    gs = torch.randn(soft.shape, device=cuda_device, generator=gen) if which != "logits" else None
+    scale = D ** -0.5
+    for prior in (True, False):
+        ref = _torch_ds(s, soft.detach(), gl, gs, scale, prior)
+        out = loglik_backward_ds(s, soft.detach(), gl, gs, scale, prior)
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        err = (out.double() - ref).abs().max().item()
+        assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (T2, which, prior, err)
+        out16 = loglik_backward_ds(s, soft.detach(), gl, gs, scale, prior, out_dtype=torch.bfloat16)
+        assert (out16.double() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_backward_bf16_operands(cuda_device):
+    """bf16 Q, K: gradients arrive in bf16 and agree with the fp32 route to bf16 accuracy."""
+    B, T1, T2, D = 2, 96, 40, 64
+    tl, ml = synth.lengths(B, T2, T1, True, 9)
+    qn, kn = synth.encoded_pair(B, T1, T2, D, tl, ml, 10)
+    tlt, mlt = torch.from_numpy(tl).to(cuda_device), torch.from_numpy(ml).to(cuda_device)
+    grads = {}
+    for dt in (torch.float32, torch.bfloat16):
+        q = torch.from_numpy(qn).to(cuda_device).to(dt).requires_grad_(True)
+        k = torch.from_numpy(kn).to(cuda_device).to(dt).requires_grad_(True)
+        soft, logits = loglik_forward(q, k, tlt, mlt)
+        torch.manual_seed(0)
+        w1 = torch.randn_like(soft); w2 = torch.randn_like(logits)
+        (soft * w1).sum().add((logits * w2).sum()).backward()
+        assert q.grad.dtype == dt and k.grad.dtype == dt
+        grads[dt] = (q.grad.float(), k.grad.float())
+    for a, b_ in zip(grads[torch.float32], grads[torch.bfloat16]):
+        assert (a - b_).abs().max() <= 0.05 * a.abs().max() + 0.05
