@@ -377,7 +377,7 @@ def run_ours(args, w):
                 "frac": kern[dom]["hbm_frac"], "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)"}
 
     n_cpu = min(B, 32)
-    cpu, _ = cpu_baseline(w, n_cpu, reps=3)
+    cpu = None if args.no_cpu else cpu_baseline(w, n_cpu, reps=3)[0]
 
     utts = world * B * args.steps
     valid_cells = float((tl * ml).sum()) * world * args.steps
@@ -419,9 +419,14 @@ def main():
     ap.add_argument("--mas-ring", type=int, default=0, help="tuning: MAS logit rows in flight, 0 = heuristic")
     ap.add_argument("--mas-slots", type=int, default=0, help="tuning: utterances per CTA (1|2), 0 = heuristic")
     ap.add_argument("--no-backward", action="store_true", help="skip the f-1 backward measurement that follows the timed steps")
+    ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (cfg5 sweep: 64..4096 with the cfg3 length law); 0 = the workload's own")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (sweeps)")
     args = ap.parse_args()
     from isp_tts_b200 import synth
     w = synth.WORKLOADS[args.workload]
+    if args.batch > 0:
+        import dataclasses
+        w = dataclasses.replace(w, batch=args.batch, name=w.name.replace("batch 256", f"batch {args.batch}") + f" [batch {args.batch}]")
     if args.impl == "reference":
         run_reference(args, w)
     else:

@@ -75,8 +75,8 @@ constexpr int kW = 32 * kC;           // columns per strip warp
 constexpr int kMaxStages = 16;
 constexpr int kMinStages = 5;         // 4 live + 1 in flight
 constexpr int kMaxStrips = 5;         // ISP_MAS_MAX_T2 / kW
-constexpr int kMaxSlots = 2;
-constexpr int kMaxThreads = 352;      // slots * (2 * strips + 1) warps <= 11
+constexpr int kMaxSlots = 3;
+constexpr int kMaxThreads = 480;      // slots * (2 * strips + 1) warps <= 15 (3 slots x 2 strips; 1 slot x 5 strips = 11)
 constexpr int kBnd = 128;             // rows in a strip-boundary ring
 constexpr int kBndChunks = kBnd / kR; // = 8, power of two
 constexpr int kZeroPage = 4096;       // bytes of zeros behind the bulk zero-fill
@@ -867,10 +867,13 @@ static int mas_plan(int B, int T1max, int T2max, MasPlan* pl) {
     const size_t fixed = kSlotHdr + (ns > 1 ? 4 * size_t(ns - 1) * kBnd : 0) + kZeroPage;
     // one utterance per CTA while every utterance still gets its own SM; two beyond that, so
     // that co-resident chains sit on different sub-partitions of one SM
+    // (A third utterance per CTA is supported -- "mas.slots" = 3 -- but measured slower than two even at 28 utterances
+    // per SM: its ring leaves 5 stages, one more than the lane skew keeps live.)
     int slots = g_opt_slots > 0 ? g_opt_slots : (B > sm_count ? 2 : 1);
     if (slots > kMaxSlots) slots = kMaxSlots;
     while (slots > 1 && 32 * slots * (2 * ns + 1) > kMaxThreads) --slots;
-    if (slots > 1 && 2 * ns > 4) slots = 1;        // more strip warps than sub-partitions: co-residency buys nothing
+    if (slots == 2 && 2 * ns > 4) slots = 1;       // more strip warps than sub-partitions: co-residency buys a chain nothing
+    if (slots == 3 && ns > 2) slots = 1;
     for (;; --slots) {
         const size_t budget = (smem_limit / slots) & ~size_t(127);
         int stg[2] = {0, 0};                      // [0]: bits in the workspace, [1]: bits in shared memory

@@ -40,7 +40,7 @@ def _reset_options():
 
 # kernel variants: backpointer bits in shared memory or in the workspace, tiled TMA or 4 B async copies,
 # one or two utterances per CTA
-MODES = {"auto": {}, "bits_global": {"mas.bits_global": 1}, "no_tma": {"mas.no_tma": 1},
+MODES = {"auto": {}, "three_slots": {"mas.slots": 3}, "bits_global": {"mas.bits_global": 1}, "no_tma": {"mas.no_tma": 1},
          "two_slots": {"mas.slots": 2}, "two_slots_global_no_tma": {"mas.slots": 2, "mas.bits_global": 1, "mas.no_tma": 1}}
 
 
