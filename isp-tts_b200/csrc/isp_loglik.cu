@@ -11,16 +11,19 @@
 //             128 B swizzle, one mbarrier per 128 B-wide K-slab), then tcgen05.mma
 //             (kind::f16 for bf16 operands, kind::tf32 for fp32 operands) issued by one
 //             elected lane, accumulating S = Q.K^T in TMEM (128 lanes x <=512 columns).
-//   warps 1-4: epilogue, one thread per frame (TMEM lane).  The row never leaves the SM:
-//             pass 1 reads S from TMEM and keeps an online max / sum-of-exp (log_softmax
-//             denominator, padded columns added in closed form) plus the prior's row sum;
-//             pass 2 re-reads S, forms attn_logits = S - lse + log(p + 1e-6) with the
-//             Gaussian prior evaluated in registers, and stashes w = exp(S-m)*(p+1e-6)
-//             back into TMEM; pass 3 turns w into attn_soft = w / sum(w).  Tiles are
-//             transposed through shared memory so that global stores are 16 B, coalesced.
+//   warps 1-8: epilogue, two threads per frame: warps w and w+4 share a TMEM lane quadrant and take
+//             the even / odd 16-column chunks; row statistics meet in shared memory.  The row never
+//             leaves the SM: pass 1 reads S from TMEM and keeps an online max / sum-of-exp
+//             (log_softmax denominator, padded columns added in closed form) plus the prior's row
+//             sum; pass 2 re-reads S, forms attn_logits = S - lse + log(p + 1e-6) with the Gaussian
+//             prior evaluated in registers, and stashes w = exp(S-m)*(p+1e-6) back into TMEM;
+//             pass 3 turns w into attn_soft = w / sum(w).  Chunks are transposed through shared
+//             memory so that global stores are 16 B, coalesced.
 // Two CTAs are resident per SM (256 TMEM columns each) when T2max <= 256, so one CTA's
 // loads and MMAs hide under the other's epilogue.  The kernel is bound by the 8 B/cell of
-// fp32 output it must write, not by the tensor pipe.
+// fp32 output it must write, not by the tensor pipe.  Padding never
+// reaches the arithmetic: a tile without a valid frame is a straight constant fill by the
+// whole CTA, a chunk of padded tokens one constant per row.
 //
 // Contract on the operands: Q rows >= mel_len[b] and K rows >= text_len[b] are zero (the
 // reference guarantees it, alignment.py:75-76).  The kernel uses it to treat padded text
@@ -321,22 +324,7 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const bool vec4 = p.vec4 != 0;
         const int nchunks_all = (p.T2max + kCW - 1) / kCW;
 
-        if (all_padding) {
-            // S == 0 on the whole tile: lse = log(T2max); attn_logits = -lse + log(1e-6); attn_soft = 0
-            const float cst = kLogPriorFloor - logf(float(p.T2max));
-            for (int ch = half; ch < nchunks_all; ch += 2) {
-#pragma unroll
-                for (int k = 0; k < kCW; ++k) my_stage[k] = p.prior ? cst : 0.0f;
-                __syncwarp();
-                store_chunk(stage, g_logits, lane, warp_row0, rows_valid, ch * kCW, p.T2max, vec4);
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < kCW; ++k) my_stage[k] = 0.0f;
-                __syncwarp();
-                store_chunk(stage, g_soft, lane, warp_row0, rows_valid, ch * kCW, p.T2max, vec4);
-                __syncwarp();
-            }
-        } else {
+        {
             // j / T2_b exactly as the reference divides (alignment.py:22), once per CTA
             const float t2f = float(T2b);
             for (int j = threadIdx.x - 32; j < p.npad; j += 32 * kEpiWarps) gt[j] = __fdiv_rn(float(j), t2f);
