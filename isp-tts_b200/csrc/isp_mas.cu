@@ -894,6 +894,10 @@ static int mas_plan(int B, int T1max, int T2max, MasPlan* pl) {
                 if (want < kMinStages) want = kMinStages;
                 if (want < nstg) nstg = want;
             }
+            // the backtrack lays its row-major ring (16 blocks) and the converters' staging buffers over the logits ring
+            const size_t nwp = size_t((T2max + 31) / 32) | 1;
+            const size_t bt_bytes = ((16 * 32 * nwp * 4 + 127) & ~size_t(127)) + (in_smem ? 0 : size_t(2 * ns - 1) * 2 * 9 * ns * 128);
+            if (bt_bytes > size_t(nstg) * stage_bytes) { if (slots == 1) break; continue; }
             pl->slots = slots;
             pl->nstg = nstg;
             pl->bits_smem = in_smem != 0;

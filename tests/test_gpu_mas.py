@@ -201,3 +201,14 @@ def test_out_of_contract_lengths_are_reported(cuda_device):
 def test_cpu_tensor_is_rejected():
     with pytest.raises(_lib.IspError):
         mas_forward(torch.zeros(1, 4, 4), torch.tensor([4]), torch.tensor([4]))
+
+
+def test_several_waves_of_ctas(cuda_device):
+    """More utterances than 2 x #SMs (the cfg5 sweep's regime): CTAs come in waves and leave in any order."""
+    B, T1, T2 = 700, 150, 72
+    x = synth.noise_logits(B, T1, T2, 21, quantize=0.25)
+    tl, ml = synth.lengths(B, T2, T1, True, 22)
+    hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, "B=700")
+    assert np.array_equal(dur.sum(1), ml)
