@@ -203,12 +203,15 @@ def test_cpu_tensor_is_rejected():
         mas_forward(torch.zeros(1, 4, 4), torch.tensor([4]), torch.tensor([4]))
 
 
-def test_several_waves_of_ctas(cuda_device):
-    """More utterances than 2 x #SMs (the cfg5 sweep's regime): CTAs come in waves and leave in any order."""
-    B, T1, T2 = 700, 150, 72
+@pytest.mark.parametrize("T2,mode", [(72, "auto"), (72, "bits_global"), (160, "auto"), (160, "bits_global"), (160, "no_tma")])
+def test_slots_take_several_utterances(cuda_device, T2, mode):
+    """More utterances than 2 x #SMs (the cfg5 sweep's regime): every persistent slot aligns several utterances
+    in a row, with one strip (72 tokens) or two (160), bits in shared memory or in the workspace."""
+    set_mode(mode)
+    B, T1 = 700, 150
     x = synth.noise_logits(B, T1, T2, 21, quantize=0.25)
     tl, ml = synth.lengths(B, T2, T1, True, 22)
     hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
-    assert_same(hard, dur, rh, rd, "B=700")
+    assert_same(hard, dur, rh, rd, f"B=700 T2={T2} {mode}")
     assert np.array_equal(dur.sum(1), ml)
