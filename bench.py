@@ -344,7 +344,24 @@ def run_ours(args, w):
                                           "gbs": by_ds / float(np.mean(t_ds)) / 1e6},
                "library_gemms_ms": {"scores_QKt": float(np.mean(t_s)), "dQ_and_dK": float(np.mean(t_mm))},
                "total_ms": float(np.mean(t_s) + np.mean(t_ds) + np.mean(t_mm))}
-        del soft_b, logits_b, g_l, g_s, sc, d_s, gq, gk
+        # f-3: binarization loss from the path vs the reference's boolean-mask gather on the dense tensors (loss.py:97-105)
+        from isp_tts_b200.mas import binarization_loss
+        hard_b, dur_b, path_b = mas_forward(logits_b, tl_dev, ml_dev, return_path=True)
+        t_ours, t_ref = [], []
+        for it in range(6):
+            ev[0].record()
+            l1 = binarization_loss(soft_b, path_b, ml_dev)
+            ev[1].record()
+            l2 = -torch.log(torch.clamp(soft_b[hard_b == 1], min=1e-6)).sum() / hard_b.sum()
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                t_ours.append(ev[0].elapsed_time(ev[1])); t_ref.append(ev[1].elapsed_time(ev[2]))
+        if abs(float(l1) - float(l2)) > 1e-4 * max(1.0, abs(float(l2))):
+            raise RuntimeError("binarization loss from the path differs from the dense formula")
+        bwd["f-3 binarization loss"] = {"isp_bin_loss_sums_ms": float(np.mean(t_ours)), "torch_dense_mask_ms": float(np.mean(t_ref)),
+                                        "value": float(l1)}
+        del soft_b, logits_b, g_l, g_s, sc, d_s, gq, gk, hard_b, dur_b, path_b
 
     if rank != 0:
         if world > 1:

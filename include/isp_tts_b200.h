@@ -83,6 +83,19 @@ int    isp_mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
                        int B, int T1max, int T2max,
                        int16_t* attn_hard, int64_t* durations,
                        void* ws, size_t ws_bytes, void* stream);
+/* Same, and also the path as one column index per frame: path (B, T1max) int16, -1 for frames past mel_len.
+ * Consumers that only need "which token does frame i belong to" (the binarization loss below, the length
+ * regulator, per-token averaging) read this instead of the dense attn_hard. */
+int    isp_mas_forward_path(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
+                            const int64_t* text_len, const int64_t* mel_len,
+                            int B, int T1max, int T2max,
+                            int16_t* attn_hard, int64_t* durations, int16_t* path,
+                            void* ws, size_t ws_bytes, void* stream);
+/* Attention binarization loss from the path (tts/models/acoustic/loss.py:97-105):
+ * sums[0] = sum over valid frames of log(max(attn_soft[b, i, path[b, i]], eps)), sums[1] = number of valid frames;
+ * the loss is -sums[0] / sums[1].  sums: 2 floats on the device, zeroed by the call. */
+int    isp_bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t* mel_len,
+                         int B, int T1max, int T2max, float eps, float* sums, void* stream);
 /* Reads back (synchronously, after the stream drains) how many utterances had a length
  * outside [1, Tmax] in the last isp_mas_forward that used `ws`.  -1 on error. */
 int    isp_mas_status(const void* ws, void* stream);

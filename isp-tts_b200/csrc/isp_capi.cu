@@ -47,8 +47,21 @@ size_t isp_mas_workspace_bytes(int B, int T1max, int T2max) { return isp::mas_wo
 int isp_mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2, const int64_t* text_len,
                     const int64_t* mel_len, int B, int T1max, int T2max, int16_t* attn_hard, int64_t* durations,
                     void* ws, size_t ws_bytes, void* stream) {
-    return isp::mas_forward(logp, sB, sT1, sT2, text_len, mel_len, B, T1max, T2max, attn_hard, durations, ws,
+    return isp::mas_forward(logp, sB, sT1, sT2, text_len, mel_len, B, T1max, T2max, attn_hard, durations, nullptr, ws,
                             ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int isp_mas_forward_path(const float* logp, int64_t sB, int64_t sT1, int64_t sT2, const int64_t* text_len,
+                         const int64_t* mel_len, int B, int T1max, int T2max, int16_t* attn_hard, int64_t* durations,
+                         int16_t* path, void* ws, size_t ws_bytes, void* stream) {
+    if (!path) { isp::set_error("isp_mas_forward_path: null path"); return ISP_ERR_INVALID; }
+    return isp::mas_forward(logp, sB, sT1, sT2, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws,
+                            ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int isp_bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t* mel_len, int B, int T1max, int T2max,
+                      float eps, float* sums, void* stream) {
+    return isp::bin_loss_sums(attn_soft, path, mel_len, B, T1max, T2max, eps, sums, static_cast<cudaStream_t>(stream));
 }
 
 int isp_mas_status(const void* ws, void* stream) {

@@ -16,7 +16,9 @@ int  cuda_fail(cudaError_t e, const char* what);
 size_t mas_workspace_bytes(int B, int T1max, int T2max);
 int    mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
                    const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
-                   int16_t* attn_hard, int64_t* durations, void* ws, size_t ws_bytes, cudaStream_t stream);
+                   int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, size_t ws_bytes, cudaStream_t stream);
+int    bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t* mel_len, int B, int T1max, int T2max,
+                     float eps, float* sums, cudaStream_t stream);
 int    mas_set_option(const char* key, int value, int* prev);
 
 size_t loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);

@@ -93,7 +93,8 @@ struct MasParams {
     int64_t* dur;
     uint32_t* bits_ws;     // global backpointer bits (BITS_SMEM == false)
     int64_t bits_stride;   // words per utterance in bits_ws
-    int16_t* path_ws;      // (B, T1max) int16: the path's column per row, until the zero-fill has landed
+    int16_t* path_ws;      // (B, T1max) int16: the path's column per row, until the zero-fill has landed (the caller's `path` if given)
+    int path_fill;         // 1: path_ws is the caller's output: frames past mel_len get -1
     int* status;           // count of utterances with out-of-contract lengths
     long long* probe;      // clock64 stamps of utterance 0 (tools/mas_probe.py)
     int ns;                // strip warps per utterance
@@ -565,6 +566,10 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             int64_t* d = p.dur + size_t(b) * p.T2max;
             for (int j = lane; j < p.T2max; j += 32) d[j] = 0;
         }
+        if (p.path_fill) {
+            int16_t* pp = p.path_ws + size_t(b) * p.T1max;
+            for (int r = n + lane; r < p.T1max; r += 32) pp[r] = -1;
+        }
         // The filler takes no part in the backtrack: it announces itself at the slot's barrier now (its plain stores above are
         // ordered before the barrier completes) and keeps filling while the others go on.
         __syncwarp();
@@ -968,7 +973,7 @@ static int launch_one(const MasMaps& maps, const MasParams& p, const MasPlan& pl
 
 int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
                 const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
-                int16_t* attn_hard, int64_t* durations, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (!logp || !text_len || !mel_len || !attn_hard || !ws) { set_error("isp_mas_forward: null pointer"); return ISP_ERR_INVALID; }
     if (B <= 0 || T1max <= 0 || T2max <= 0) { set_error("isp_mas_forward: B, T1max, T2max must be positive"); return ISP_ERR_INVALID; }
     if (sT2 != 1) { set_error("isp_mas_forward: sT2 must be 1 (token axis contiguous), got %lld", (long long)sT2); return ISP_ERR_INVALID; }
@@ -994,7 +999,8 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
     p.probe = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + 64);
     p.bits_ws = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 256);
     p.bits_stride = int64_t(pl.bits_words);
-    p.path_ws = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(ws) + 256 + size_t(B) * pl.bits_words * 4);
+    p.path_ws = path ? path : reinterpret_cast<int16_t*>(reinterpret_cast<char*>(ws) + 256 + size_t(B) * pl.bits_words * 4);
+    p.path_fill = path ? 1 : 0;
     p.ns = pl.ns; p.slots = pl.slots; p.nstg = pl.nstg; p.wlast = pl.wlast;
     p.slot_bytes = int(pl.slot_bytes); p.dbg = g_opt_dbg;
     MasMaps maps;

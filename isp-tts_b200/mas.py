@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["mas_forward", "b_mas", "cuda_b_mas", "mas_durations"]
+__all__ = ["mas_forward", "b_mas", "cuda_b_mas", "mas_durations", "binarization_loss"]
 
 
 def _as_len(t, device, name):
@@ -32,13 +32,14 @@ def _as_len(t, device, name):
 
 
 def mas_forward(attn_logits: torch.Tensor, text_len, mel_len, *, attn_out: torch.Tensor | None = None,
-                durations: bool = True, check_lengths: bool = False):
+                durations: bool = True, check_lengths: bool = False, return_path: bool = False):
     """MAS + hard path + durations in one launch.
 
     attn_logits (B, T1max, T2max) fp32 CUDA tensor (rows = mel frames); not modified.
     text_len = in_lens, mel_len = out_lens (int64).  Returns (attn_hard int16
     (B, T1max, T2max), durations int64 (B, T2max) or None).  Enqueued on the
-    current stream; no host synchronisation unless check_lengths=True.
+    current stream; no host synchronisation unless check_lengths=True.  With return_path=True a third
+    value follows: the path as one token index per frame, int16 (B, T1max), -1 past mel_len.
     """
     if attn_logits.dim() != 3:
         raise ValueError("attn_logits must be (B, T1max, T2max)")
@@ -66,15 +67,59 @@ def mas_forward(attn_logits: torch.Tensor, text_len, mel_len, *, attn_out: torch
         ws_bytes = lib.isp_mas_workspace_bytes(B, T1, T2)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.isp_mas_forward(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), tl.data_ptr(), ml.data_ptr(),
-                                 B, T1, T2, hard.data_ptr(), dur.data_ptr() if dur is not None else None,
-                                 ws.data_ptr(), ws_bytes, stream)
+        path = torch.empty((B, T1), dtype=torch.int16, device=dev) if return_path else None
+        if return_path:
+            rc = lib.isp_mas_forward_path(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), tl.data_ptr(), ml.data_ptr(),
+                                          B, T1, T2, hard.data_ptr(), dur.data_ptr() if dur is not None else None,
+                                          path.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+        else:
+            rc = lib.isp_mas_forward(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), tl.data_ptr(), ml.data_ptr(),
+                                     B, T1, T2, hard.data_ptr(), dur.data_ptr() if dur is not None else None,
+                                     ws.data_ptr(), ws_bytes, stream)
         _lib.check(rc, "isp_mas_forward")
         if check_lengths:
             bad = lib.isp_mas_status(ws.data_ptr(), stream)
             if bad != 0:
                 raise _lib.IspError(f"{bad} utterance(s) have a length outside [1, Tmax] (out of contract, SURVEY.md A.6)")
-    return hard, dur
+    return (hard, dur, path) if return_path else (hard, dur)
+
+
+class _BinLoss(torch.autograd.Function):
+    """tts/models/acoustic/loss.py:97-105 from the path: forward = one gather of sum(mel_len) floats
+    (isp_bin_loss_sums); backward = -1 / (count * soft) on the path's cells, 0 elsewhere."""
+
+    @staticmethod
+    def forward(ctx, attn_soft, path, mel_len, eps):
+        dev = attn_soft.device
+        _lib.require_device(dev)
+        lib = _lib.load()
+        soft = attn_soft.detach().float().contiguous()
+        B, T1, T2 = soft.shape
+        ml = _as_len(mel_len, dev, "mel_len")
+        sums = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.isp_bin_loss_sums(soft.data_ptr(), path.data_ptr(), ml.data_ptr(), B, T1, T2, float(eps),
+                                       sums.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "isp_bin_loss_sums")
+        ctx.save_for_backward(soft, path, sums)
+        ctx.eps = float(eps)
+        return -sums[0] / sums[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        soft, path, sums = ctx.saved_tensors
+        idx = path.clamp(min=0).long().unsqueeze(-1)
+        at = soft.gather(2, idx)
+        val = torch.where((path.unsqueeze(-1) >= 0) & (at > ctx.eps), -g / (sums[1] * at), torch.zeros_like(at))
+        return torch.zeros_like(soft).scatter_(2, idx, val), None, None, None
+
+
+def binarization_loss(attn_soft: torch.Tensor, path: torch.Tensor, mel_len, eps: float = 1e-6) -> torch.Tensor:
+    """Drop-in value for AttentionBinarizationLoss.forward(soft_attention, hard_attention) (loss.py:97-105), taking the
+    path (mas_forward(..., return_path=True)) instead of the dense hard attention."""
+    if path.dtype != torch.int16 or path.shape != attn_soft.shape[:2] or not path.is_contiguous():
+        raise ValueError("path must be the contiguous int16 (B, T1max) tensor returned by mas_forward(..., return_path=True)")
+    return _BinLoss.apply(attn_soft, path, mel_len, eps)
 
 
 def mas_durations(attn_logits, text_len, mel_len):

@@ -215,3 +215,31 @@ def test_slots_take_several_utterances(cuda_device, T2, mode):
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
     assert_same(hard, dur, rh, rd, f"B=700 T2={T2} {mode}")
     assert np.array_equal(dur.sum(1), ml)
+
+
+def test_path_output_and_binarization_loss(cuda_device):
+    """isp_mas_forward_path + isp_bin_loss_sums against the reference formula on the dense tensors
+    (tts/models/acoustic/loss.py:97-105), value and gradient."""
+    from isp_tts_b200.mas import binarization_loss
+    B, T1, T2 = 5, 140, 36
+    x = synth.noise_logits(B, T1, T2, 31)
+    tl, ml = synth.lengths(B, T2, T1, True, 32)
+    xt = torch.from_numpy(x).to(cuda_device)
+    mlt = torch.from_numpy(ml).to(cuda_device)
+    hard, dur, path = mas_forward(xt, torch.from_numpy(tl), mlt, return_path=True)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard.cpu().numpy(), dur.cpu().numpy(), rh, rd, "path run")
+    ref_path = omas.path_from_hard(rh, ml).astype(np.int64)
+    got = path.cpu().numpy().astype(np.int64)
+    for b in range(B):
+        assert np.array_equal(got[b, :ml[b]], ref_path[b, :ml[b]]) and np.all(got[b, ml[b]:] == -1)
+    # a soft attention with some entries below eps on the path
+    soft = torch.softmax(xt * 3.0, dim=2)
+    soft = (soft * (soft > 1e-3)).detach().requires_grad_(True)
+    loss = binarization_loss(soft, path, mlt)
+    loss.backward()
+    soft2 = soft.detach().clone().requires_grad_(True)
+    ref = -torch.log(torch.clamp(soft2[hard == 1], min=1e-6)).sum() / hard.sum()
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+    assert torch.allclose(soft.grad, soft2.grad, rtol=1e-5, atol=1e-7)
