@@ -361,7 +361,30 @@ def run_ours(args, w):
             raise RuntimeError("binarization loss from the path differs from the dense formula")
         bwd["f-3 binarization loss"] = {"isp_bin_loss_sums_ms": float(np.mean(t_ours)), "torch_dense_mask_ms": float(np.mean(t_ref)),
                                         "value": float(l1)}
-        del soft_b, logits_b, g_l, g_s, sc, d_s, gq, gk, hard_b, dur_b, path_b
+        # f-3: length regulator from the path vs the reference's matmul with a (T1 x T2) 0/1 matrix (temporal_adaptor.py:420-431)
+        from isp_tts_b200.consumers import length_regulate
+        enc_dim = 384                                   # recipes/acoustic/core.yaml: encoder dim
+        xe = torch.randn((B, T2, enc_dim), device=dev, generator=gen)
+        t_ours, t_ref = [], []
+        for it in range(6):
+            ev[0].record()
+            o1 = length_regulate(xe, path_b, dur_b)
+            ev[1].record()
+            reps = (dur_b.float() + 0.5).long()
+            cums = torch.cumsum(torch.nn.functional.pad(reps, (1, 0, 0, 0), value=0.0), dim=1, dtype=xe.dtype)[:, None, :]
+            r = torch.arange(int(T1), device=dev)[None, :, None]
+            o2 = torch.matmul(((cums[:, :, :-1] <= r) & (cums[:, :, 1:] > r)).to(xe.dtype), xe)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                t_ours.append(ev[0].elapsed_time(ev[1])); t_ref.append(ev[1].elapsed_time(ev[2]))
+        if not torch.equal(o1, o2):
+            raise RuntimeError("length regulator from the path differs from the reference formula")
+        by_lr = 4 * B * T1 * enc_dim + 2 * B * T1
+        bwd["f-3 length regulator"] = {"isp_length_regulate_ms": float(np.mean(t_ours)), "algorithmic_bytes": by_lr,
+                                       "gbs": by_lr / float(np.mean(t_ours)) / 1e6, "torch_reference_ms": float(np.mean(t_ref)),
+                                       "shape": f"x ({B}, {T2}, {enc_dim}) fp32 -> ({B}, {T1}, {enc_dim})"}
+        del soft_b, logits_b, g_l, g_s, sc, d_s, gq, gk, hard_b, dur_b, path_b, xe, o1, o2
 
     if rank != 0:
         if world > 1:
@@ -371,6 +394,7 @@ def run_ours(args, w):
     hbm_peak, tf_peak, which = load_peaks()
     if bwd is not None:
         bwd["isp_loglik_backward_ds"]["hbm_frac"] = bwd["isp_loglik_backward_ds"]["gbs"] / hbm_peak
+        bwd["f-3 length regulator"]["hbm_frac"] = bwd["f-3 length regulator"]["gbs"] / hbm_peak
     by_mas = mas_bytes(tl, ml, B, T1, T2)
     by_ll = loglik_bytes(B, T1, T2, D, elem)
     fl_ll = loglik_flops(B, T1, T2, D)

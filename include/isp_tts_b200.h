@@ -96,6 +96,15 @@ int    isp_mas_forward_path(const float* logp, int64_t sB, int64_t sT1, int64_t 
  * the loss is -sums[0] / sums[1].  sums: 2 floats on the device, zeroed by the call. */
 int    isp_bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t* mel_len,
                          int B, int T1max, int T2max, float eps, float* sums, void* stream);
+/* Length regulator from the path (tts/models/acoustic/modules/temporal_adaptor.py:411-436, `durations` branch):
+ * out[b, t, :] = x[b, path[b, t], :] for the utterance's frames, 0 after.  x (B, T2max, C), out (B, T1max, C), fp32 or
+ * bf16 (dtype = ISP_DTYPE_*), contiguous, 16 B aligned, C * elem % 16 == 0.
+ * Backward (fp32): gx[b, j, :] = sum of g[b, t, :] over starts[b, j] <= t < starts[b, j] + durations[b, j]
+ * (starts = exclusive cumulative sum of durations along the token axis; both (B, T2max) int64). */
+int    isp_length_regulate(const void* x, const int16_t* path, void* out, int dtype,
+                           int B, int T1max, int T2max, int C, void* stream);
+int    isp_length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
+                                    int B, int T1max, int T2max, int C, void* stream);
 /* Reads back (synchronously, after the stream drains) how many utterances had a length
  * outside [1, Tmax] in the last isp_mas_forward that used `ws`.  -1 on error. */
 int    isp_mas_status(const void* ws, void* stream);

@@ -16,7 +16,7 @@ ISP_DTYPE_BF16 = 1
 
 EXPORTS = [
     "isp_version", "isp_last_error", "isp_device_check",
-    "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_mas_status",
+    "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_mas_status",
     "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_set_option",
 ]
 
@@ -49,6 +49,10 @@ def load():
     lib.isp_mas_forward_path.restype = c_int
     lib.isp_bin_loss_sums.argtypes = [vp, vp, vp, c_int, c_int, c_int, f32, vp, vp]
     lib.isp_bin_loss_sums.restype = c_int
+    lib.isp_length_regulate.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.isp_length_regulate.restype = c_int
+    lib.isp_length_regulate_backward.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp]
+    lib.isp_length_regulate_backward.restype = c_int
     lib.isp_mas_status.argtypes = [vp, vp]
     lib.isp_mas_status.restype = c_int
     lib.isp_loglik_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]

@@ -1,0 +1,75 @@
+"""Consumers of the alignment that take the path from the MAS kernel.
+
+Reference (paths relative to the reference root):
+  LengthRegulator.forward(x, durations)     tts/models/acoustic/modules/temporal_adaptor.py:411-436
+  AttentionBinarizationLoss.forward         tts/models/acoustic/loss.py:97-105   (isp_tts_b200.mas.binarization_loss)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+__all__ = ["length_regulate", "LengthRegulator"]
+
+
+class _LengthRegulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, path, durations):
+        dev = x.device
+        _lib.require_device(dev)
+        lib = _lib.load()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("x must be float32 or bfloat16")
+        x = x.contiguous()
+        B, T2, C = x.shape
+        T1 = path.shape[1]
+        out = torch.empty((B, T1, C), dtype=x.dtype, device=dev)
+        dt = _lib.ISP_DTYPE_BF16 if x.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+        with torch.cuda.device(dev):
+            rc = lib.isp_length_regulate(x.data_ptr(), path.data_ptr(), out.data_ptr(), dt, B, T1, T2, C,
+                                         torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "isp_length_regulate")
+        ctx.save_for_backward(durations)
+        ctx.shape = (B, T1, T2, C)
+        ctx.dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (durations,) = ctx.saved_tensors
+        B, T1, T2, C = ctx.shape
+        lib = _lib.load()
+        dev = g.device
+        g32 = g.float().contiguous()
+        dur = durations.to(torch.int64).contiguous()
+        starts = (torch.cumsum(dur, dim=1) - dur).contiguous()
+        gx = torch.empty((B, T2, C), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.isp_length_regulate_backward(g32.data_ptr(), dur.data_ptr(), starts.data_ptr(), gx.data_ptr(), B, T1, T2, C,
+                                                  torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "isp_length_regulate_backward")
+        return gx.to(ctx.dtype), None, None
+
+
+def length_regulate(x: torch.Tensor, path: torch.Tensor, durations: torch.Tensor) -> torch.Tensor:
+    """x (B, T2, C) expanded to frames: out[b, t] = x[b, path[b, t]] (0 past the utterance).  `path` and `durations`
+    are what mas_forward(..., return_path=True) returned for the same batch."""
+    if path.dtype != torch.int16 or not path.is_contiguous():
+        raise ValueError("path must be the contiguous int16 (B, T1max) tensor returned by mas_forward(..., return_path=True)")
+    return _LengthRegulate.apply(x, path, durations)
+
+
+class LengthRegulator(torch.nn.Module):
+    """Same call as the reference module when it is fed hard durations (temporal_adaptor.py:411-436), plus `path`:
+    forward(x, durations, max_len=None, path=...) -> (out, dec_lens)."""
+
+    def forward(self, x, durations, max_len=None, path=None):
+        if path is None:
+            raise _lib.IspError("LengthRegulator needs the path from mas_forward(..., return_path=True); there is no CPU / dense fallback")
+        dec_lens = (durations.float() + 0.5).long().sum(dim=1)
+        out = length_regulate(x, path, durations)
+        if max_len is not None:
+            out = out[:, :max_len]
+            dec_lens = torch.clamp_max(dec_lens, max_len)
+        return out, dec_lens

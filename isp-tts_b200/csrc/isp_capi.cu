@@ -90,6 +90,15 @@ int isp_loglik_backward_ds(const float* S, const float* attn_soft, const float* 
                                    static_cast<cudaStream_t>(stream));
 }
 
+int isp_length_regulate(const void* x, const int16_t* path, void* out, int dtype, int B, int T1max, int T2max, int C, void* stream) {
+    return isp::length_regulate(x, path, out, dtype, B, T1max, T2max, C, static_cast<cudaStream_t>(stream));
+}
+
+int isp_length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
+                                 int B, int T1max, int T2max, int C, void* stream) {
+    return isp::length_regulate_backward(g, durations, starts, gx, B, T1max, T2max, C, static_cast<cudaStream_t>(stream));
+}
+
 int isp_set_option(const char* key, int value) {
     if (!key) return ISP_ERR_INVALID;
     int prev = 0;

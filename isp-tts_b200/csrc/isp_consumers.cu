@@ -65,4 +65,83 @@ int bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t* me
     return 0;
 }
 
+// Length regulator, tts/models/acoustic/modules/temporal_adaptor.py:411-436 (`durations` branch): the reference builds a
+// (T1 x T2) 0/1 matrix from the cumulated durations and multiplies it with x (2*T1*T2*C flops, 4 B/cell of matrix).  Each
+// row of that matrix has a single one, at the path's column, so the product is a gather: one 16 B vector per thread,
+// x rows come from L2 (consecutive frames repeat the same token), the output is written once with streaming stores.
+__global__ void __launch_bounds__(256)
+length_regulate_kernel(const uint4* __restrict__ x, const int16_t* __restrict__ path, uint4* __restrict__ out,
+                       long long rows, int T1max, int T2max, int vec_per_row) {
+    // one warp per frame: the path entry is read once per row, no per-element division
+    const int lane = threadIdx.x & 31;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+        const int col = __ldg(path + row);
+        uint4* dst = out + row * vec_per_row;
+        if (col >= 0 && col < T2max) {
+            const uint4* src = x + ((row / T1max) * T2max + col) * vec_per_row;
+            for (int v = lane; v < vec_per_row; v += 32) st_cs_v4(dst + v, __ldg(src + v));
+        } else {
+            for (int v = lane; v < vec_per_row; v += 32) st_cs_v4(dst + v, make_uint4(0u, 0u, 0u, 0u));
+        }
+    }
+}
+
+// Backward: gx[b, j, :] = sum of g[b, t, :] over the token's frames [starts, starts + durations); one CTA per token,
+// each thread a float4 of channels, frames read in order (fixed summation order, coalesced rows).
+__global__ void __launch_bounds__(128)
+length_regulate_bwd_kernel(const float4* __restrict__ g, const int64_t* __restrict__ durations, const int64_t* __restrict__ starts,
+                           float4* __restrict__ gx, int T1max, int T2max, int vec_per_row) {
+    const long long tok = blockIdx.x;                 // b * T2max + j
+    const long long b = tok / T2max;
+    long long t0 = starts[tok], n = durations[tok];
+    if (t0 < 0) { n += t0; t0 = 0; }
+    if (t0 + n > T1max) n = T1max - t0;
+    for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* src = g + (b * T1max + t0) * vec_per_row + v;
+        for (long long t = 0; t < n; ++t) {
+            const float4 a = __ldcs(src + t * vec_per_row);
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+        gx[tok * vec_per_row + v] = acc;
+    }
+}
+
+int length_regulate(const void* x, const int16_t* path, void* out, int dtype, int B, int T1max, int T2max, int C, cudaStream_t stream) {
+    if (!x || !path || !out) { set_error("isp_length_regulate: null pointer"); return ISP_ERR_INVALID; }
+    if (B <= 0 || T1max <= 0 || T2max <= 0 || C <= 0) { set_error("isp_length_regulate: sizes must be positive"); return ISP_ERR_INVALID; }
+    if (dtype != ISP_DTYPE_F32 && dtype != ISP_DTYPE_BF16) { set_error("isp_length_regulate: dtype must be ISP_DTYPE_F32 or ISP_DTYPE_BF16"); return ISP_ERR_INVALID; }
+    const int elem = dtype == ISP_DTYPE_BF16 ? 2 : 4;
+    if ((size_t(C) * elem) % 16 != 0 || (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % 16 != 0) {
+        set_error("isp_length_regulate: rows of x / out must be whole 16 B vectors (C * elem %% 16 == 0, 16 B aligned)");
+        return ISP_ERR_INVALID;
+    }
+    const int vec = int(size_t(C) * elem / 16);
+    const long long rows = (long long)B * T1max;
+    const int grid = int(std::min<long long>((rows + 7) / 8, 148LL * 8 * 4));
+    length_regulate_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), path, static_cast<uint4*>(out), rows, T1max, T2max, vec);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "length_regulate_kernel launch");
+    return 0;
+}
+
+int length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
+                             int B, int T1max, int T2max, int C, cudaStream_t stream) {
+    if (!g || !durations || !starts || !gx) { set_error("isp_length_regulate_backward: null pointer"); return ISP_ERR_INVALID; }
+    if (B <= 0 || T1max <= 0 || T2max <= 0 || C <= 0) { set_error("isp_length_regulate_backward: sizes must be positive"); return ISP_ERR_INVALID; }
+    if (C % 4 != 0 || (reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(gx)) % 16 != 0) {
+        set_error("isp_length_regulate_backward: C must be a multiple of 4 and g / gx 16 B aligned");
+        return ISP_ERR_INVALID;
+    }
+    const long long toks = (long long)B * T2max;
+    if (toks > 0x7fffffffLL) { set_error("isp_length_regulate_backward: B * T2max too large"); return ISP_ERR_INVALID; }
+    length_regulate_bwd_kernel<<<unsigned(toks), 128, 0, stream>>>(reinterpret_cast<const float4*>(g), durations, starts,
+                                                                   reinterpret_cast<float4*>(gx), T1max, T2max, C / 4);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "length_regulate_bwd_kernel launch");
+    return 0;
+}
+
+
 }  // namespace isp

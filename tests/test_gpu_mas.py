@@ -241,5 +241,36 @@ def test_path_output_and_binarization_loss(cuda_device):
     soft2 = soft.detach().clone().requires_grad_(True)
     ref = -torch.log(torch.clamp(soft2[hard == 1], min=1e-6)).sum() / hard.sum()
     ref.backward()
-    assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+    assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
     assert torch.allclose(soft.grad, soft2.grad, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_length_regulator_from_path(cuda_device, dtype):
+    """isp_length_regulate (+ backward) against the reference's matmul with the 0/1 matrix built from the cumulated
+    durations (tts/models/acoustic/modules/temporal_adaptor.py:420-431)."""
+    from isp_tts_b200.consumers import LengthRegulator
+    B, T1, T2, C = 4, 150, 40, 48
+    x_l = synth.noise_logits(B, T1, T2, 41)
+    tl, ml = synth.lengths(B, T2, T1, True, 42)
+    mlt = torch.from_numpy(ml).to(cuda_device)
+    hard, dur, path = mas_forward(torch.from_numpy(x_l).to(cuda_device), torch.from_numpy(tl), mlt, return_path=True)
+    gen = torch.Generator(device=cuda_device).manual_seed(3)
+    x = torch.randn((B, T2, C), device=cuda_device, generator=gen).to(dtype).requires_grad_(True)
+    out, dec = LengthRegulator()(x, dur, path=path)
+    assert torch.equal(dec, mlt)
+    # reference: temporal_adaptor.py:420-431
+    x2 = x.detach().clone().float().requires_grad_(True)
+    reps = (dur.float() + 0.5).long()
+    cums = torch.cumsum(torch.nn.functional.pad(reps, (1, 0, 0, 0), value=0.0), dim=1, dtype=torch.float32)[:, None, :]
+    r = torch.arange(int(reps.sum(1).max()), device=cuda_device)[None, :, None]
+    mult = ((cums[:, :, :-1] <= r) & (cums[:, :, 1:] > r)).float()
+    ref = torch.matmul(mult, x2)
+    assert out.shape[1] == T1 and ref.shape[1] == int(ml.max())
+    assert torch.equal(out[:, :ref.shape[1]].float(), ref.to(dtype).float())           # a gather: exact
+    assert out.detach()[:, ref.shape[1]:].abs().sum().item() == 0.0
+    w = torch.randn(out.shape, device=cuda_device, generator=gen)
+    (out.float() * w).sum().backward()
+    (ref * w[:, :ref.shape[1]]).sum().backward()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert torch.allclose(x.grad.float(), x2.grad, rtol=tol, atol=tol * 10)
