@@ -51,6 +51,7 @@ constexpr float kLogPriorFloor = -13.815510557964274f;   // log(1e-6)
 constexpr float kPriorEps = 1e-6f;
 constexpr float kPriorThreshold = 1e-4f;                 // alignment.py:18
 constexpr float kNegInvTwoGammaSq = -50.0f;              // -1 / (2 * 0.1^2)
+constexpr float kPriorScale = 8.493218002880191f;        // sqrt(50 log2 e): exp(-50 x^2) = 2^(-(kPriorScale x)^2)
 
 struct LoglikParams {
     const int64_t* text_len;
@@ -325,22 +326,49 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const int nchunks_all = (p.T2max + kCW - 1) / kCW;
 
         {
-            // j / T2_b exactly as the reference divides (alignment.py:22), once per CTA
+            // j / T2_b exactly as the reference divides (alignment.py:22), once per CTA, stored pre-scaled by
+            // sqrt(50 log2 e): the Gaussian prior exp(-(g - u)^2 / (2 * 0.1^2)) is then ex2(-d * d) with d = gs[j] - us
             const float t2f = float(T2b);
-            for (int j = threadIdx.x - 32; j < p.npad; j += 32 * kEpiWarps) gt[j] = __fdiv_rn(float(j), t2f);
+            for (int j = threadIdx.x - 32; j < p.npad; j += 32 * kEpiWarps) gt[j] = __fdiv_rn(float(j), t2f) * kPriorScale;
             asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
 
             const bool row_valid = i < T1b;
-            const float u = __fdiv_rn(float(i), float(T1b));   // alignment.py:25
+            const float us = __fdiv_rn(float(i), float(T1b)) * kPriorScale;   // alignment.py:25
             const float c = p.scale * kLog2e;
             const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
             const int nchunks = nb / kCW;                      // chunks that hold MMA output (nb is a multiple of 16)
+            const uint32_t pair_bar = 2u + uint32_t(quad);     // the two warps of a TMEM quadrant meet on their own barrier
 
-            mbar_wait(mma_done, 0);
-            tc_fence_after();
+            // per-thread pieces of the staged, coalesced stores (see store_chunk_fast)
+            const int c4 = (lane & 3) * 4;
+            const int rb = lane >> 2;
+            const float* st_rd = stage + rb * kStagePitch + c4;
+            const size_t g_off = size_t(warp_row0 + rb) * p.T2max + c4;
+            const size_t g_rs = size_t(8) * p.T2max;
+            uint32_t rowok = 0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) rowok |= (rb + 8 * it < rows_valid) ? (1u << it) : 0u;
+            auto store_chunk_fast = [&](float* gout, int j0) __attribute__((always_inline)) {
+                if (vec4) {
+                    if (j0 + c4 < p.T2max) {
+                        float* gp = gout + g_off + j0;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            if (rowok & (1u << it)) {
+                                const float4 t = *reinterpret_cast<const float4*>(st_rd + it * 8 * kStagePitch);
+                                *reinterpret_cast<float4*>(gp + it * g_rs) = t;
+                            }
+                        }
+                    }
+                } else {
+                    store_chunk(stage, gout, lane, warp_row0, rows_valid, j0, p.T2max, false);
+                }
+            };
 
             float v[kCW];
             if (p.debug_scores) {
+                mbar_wait(mma_done, 0);
+                tc_fence_after();
                 for (int ch = half; ch < nchunks_all; ch += 2) {
                     if (ch < nchunks) tmem_ld16(tlane + ch * kCW, v);
 #pragma unroll
@@ -355,60 +383,74 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     __syncwarp();
                 }
             } else {
-                // ---- pass 1: online max / sum of exp over this half's valid columns; prior row sum ------
-                float m = -CUDART_INF_F, sum_e = 0.0f, psum = 0.0f;
+                // ---- pass 0: the prior's row sum over this half's valid columns.  It does not depend on the scores, so it
+                // runs while the operands are still in flight (the wait for the MMA comes after it) -------------------
+                float psum = 0.0f;
+                if (p.prior) {
+                    float ps0 = 0.0f, ps1 = 0.0f;
+                    for (int ch = half; ch < nchunks; ch += 2) {
+                        const int j0 = ch * kCW;
+                        const int kmax = min(kCW, T2b - j0);
+                        if (kmax <= 0) break;
+                        // terms below ~1e-11 of the peak cannot change an fp32 sum: skip far chunks (|g - u| > 0.71)
+                        const float dlo = gt[j0] - us, dhi = gt[j0 + kmax - 1] - us;
+                        const bool near = row_valid && dlo <= 0.71f * kPriorScale && dhi >= -0.71f * kPriorScale;
+                        if (!__any_sync(0xffffffffu, near)) continue;
+                        if (kmax == kCW) {
+#pragma unroll
+                            for (int k4 = 0; k4 < kCW / 4; ++k4) {
+                                const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
+                                const float d0 = g4.x - us, d1 = g4.y - us, d2 = g4.z - us, d3 = g4.w - us;
+                                ps0 += fast_ex2(-d0 * d0); ps1 += fast_ex2(-d1 * d1);
+                                ps0 += fast_ex2(-d2 * d2); ps1 += fast_ex2(-d3 * d3);
+                            }
+                        } else {
+                            for (int k = 0; k < kmax; ++k) { const float d = gt[j0 + k] - us; ps0 += fast_ex2(-d * d); }
+                        }
+                    }
+                    psum = row_valid ? ps0 + ps1 : 0.0f;
+                }
+
+                mbar_wait(mma_done, 0);
+                tc_fence_after();
+
+                // ---- pass 1: online max / sum of exp over this half's valid columns -------------------------------
+                float m = -CUDART_INF_F, sum_e = 0.0f;
                 for (int ch = half; ch < nchunks; ch += 2) {
                     const int j0 = ch * kCW;
                     const int kmax = min(kCW, T2b - j0);
                     if (kmax <= 0) break;
                     tmem_ld16(tlane + j0, v);
-                    const bool full = kmax == kCW;              // warp-uniform: no column masks in the common case
-                    float cm = -CUDART_INF_F;
-                    if (full) {
+                    float cm = -CUDART_INF_F, acc0 = 0.0f, acc1 = 0.0f;
+                    if (kmax == kCW) {                          // warp-uniform: no column masks in the common case
 #pragma unroll
                         for (int k = 0; k < kCW; ++k) cm = fmaxf(cm, v[k]);
+                        const float mn = fmaxf(m, cm);
+                        const float mnc = mn * c;
+#pragma unroll
+                        for (int k = 0; k < kCW; k += 2) {
+                            acc0 += fast_ex2(fmaf(v[k], c, -mnc));
+                            acc1 += fast_ex2(fmaf(v[k + 1], c, -mnc));
+                        }
+                        sum_e = fmaf(sum_e, fast_ex2((m - mn) * c), acc0 + acc1);
+                        m = mn;
                     } else {
 #pragma unroll
                         for (int k = 0; k < kCW; ++k) cm = fmaxf(cm, k < kmax ? v[k] : -CUDART_INF_F);
-                    }
-                    const float mn = fmaxf(m, cm);
-                    const float mnc = mn * c;
-                    float acc = 0.0f;
-                    if (full) {
-#pragma unroll
-                        for (int k = 0; k < kCW; ++k) acc += fast_ex2(fmaf(v[k], c, -mnc));
-                    } else {
+                        const float mn = fmaxf(m, cm);
+                        const float mnc = mn * c;
 #pragma unroll
                         for (int k = 0; k < kCW; ++k) {
                             const float e = fast_ex2(fmaf(v[k], c, -mnc));
-                            acc += k < kmax ? e : 0.0f;
+                            acc0 += k < kmax ? e : 0.0f;
                         }
-                    }
-                    sum_e = sum_e * fast_ex2((m - mn) * c) + acc;
-                    m = mn;
-                    if (p.prior) {
-                        // terms below ~1e-11 of the peak cannot change an fp32 sum: skip far chunks
-                        const float glo = gt[j0] - u, ghi = gt[j0 + kmax - 1] - u;
-                        const bool near = row_valid && glo <= 0.71f && ghi >= -0.71f;
-                        if (__any_sync(0xffffffffu, near)) {
-                            float pacc = 0.0f;
-#pragma unroll
-                            for (int k4 = 0; k4 < kCW / 4; ++k4) {
-                                const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
-                                const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float p0 = fast_ex2(gg[q] * gg[q] * (kNegInvTwoGammaSq * kLog2e));
-                                    pacc += (full || (4 * k4 + q) < kmax) ? p0 : 0.0f;
-                                }
-                            }
-                            psum += row_valid ? pacc : 0.0f;
-                        }
+                        sum_e = fmaf(sum_e, fast_ex2((m - mn) * c), acc0);
+                        m = mn;
                     }
                 }
                 // combine the two halves' statistics
                 xch[half * kTileM + r_in_tile] = make_float4(m, sum_e, psum, 0.0f);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
                 {
                     const float4 o = xch[(half ^ 1) * kTileM + r_in_tile];
                     const float mn = fmaxf(m, o.x);
@@ -428,24 +470,25 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 const float lse = m * p.scale + logf(sum_e);
                 const float mc = m * c;
                 const float inv_psum = 1.0f / (psum + 1e-5f);                  // alignment.py:34
-                // cells with g^2 above this cannot pass the 1e-4 threshold (alignment.py:35)
+                // cells with (g - u)^2 above this cannot pass the 1e-4 threshold (alignment.py:35)
                 const float thr_arg = kPriorThreshold * (psum + 1e-5f);
-                const float gband = (row_valid && p.prior && thr_arg < 1.0f)
-                                        ? sqrtf(-logf(thr_arg) * (1.0f / 50.0f)) * 1.001f + 1e-6f
+                const float dband = (row_valid && p.prior && thr_arg < 1.0f)
+                                        ? (sqrtf(-logf(thr_arg) * (1.0f / 50.0f)) * 1.001f + 1e-6f) * kPriorScale
                                         : -1.0f;
+                const float cst_pad = p.prior ? kLogPriorFloor - lse : 0.0f;   // attn_logits of a padded text column (S == 0)
 
                 // ---- pass 2: attn_logits, and w = exp(S - m) * (p + 1e-6) stashed in TMEM -------
-                float sum_w = 0.0f;
+                float sw0 = 0.0f, sw1 = 0.0f;
                 for (int ch = half; ch < nchunks_all; ch += 2) {
                     const int j0 = ch * kCW;
                     const int kmax = min(kCW, T2b - j0);                       // valid text columns here
                     if (kmax <= 0) {
                         // padded text columns only: S == 0, so attn_logits is one constant per row and w is 0
-                        const float cst = p.prior ? kLogPriorFloor - lse : 0.0f;
+                        const float4 c4v = make_float4(cst_pad, cst_pad, cst_pad, cst_pad);
 #pragma unroll
-                        for (int k = 0; k < kCW; ++k) my_stage[k] = cst;
+                        for (int k4 = 0; k4 < kCW / 4; ++k4) *reinterpret_cast<float4*>(my_stage + 4 * k4) = c4v;
                         __syncwarp();
-                        store_chunk(stage, g_logits, lane, warp_row0, rows_valid, j0, p.T2max, vec4);
+                        store_chunk_fast(g_logits, j0);
                         __syncwarp();
                         continue;
                     }
@@ -461,14 +504,11 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                             my_stage[k] = v[k] * p.scale;
                             const float e = fast_ex2(fmaf(v[k], c, -mc));
                             v[k] = (k < kmax && row_valid) ? e : 0.0f;
-                            sum_w += v[k];
+                            sw0 += v[k];
                         }
                     } else {
-                        bool near = false;
-                        if (kmax > 0) {
-                            const float glo = gt[j0] - u, ghi = gt[j0 + kmax - 1] - u;
-                            near = glo <= gband && ghi >= -gband;
-                        }
+                        const float dlo = gt[j0] - us, dhi = gt[j0 + kmax - 1] - us;
+                        const bool near = dlo <= dband && dhi >= -dband;
                         // warp-uniform: every column of the chunk is a valid token and every row of the warp a valid frame
                         const bool full = kmax == kCW && __all_sync(0xffffffffu, row_valid);
                         if (__any_sync(0xffffffffu, near)) {
@@ -476,45 +516,54 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
                                 for (int k4 = 0; k4 < kCW / 4; ++k4) {
                                     const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
-                                    const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
+                                    const float dd[4] = {g4.x - us, g4.y - us, g4.z - us, g4.w - us};
+                                    float lg[4];
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
                                         const int k = 4 * k4 + q;
-                                        float pr = fast_ex2(gg[q] * gg[q] * (kNegInvTwoGammaSq * kLog2e)) * inv_psum;
+                                        float pr = fast_ex2(-dd[q] * dd[q]) * inv_psum;
                                         pr = pr >= kPriorThreshold ? pr : 0.0f;
                                         const float P = pr + kPriorEps;
-                                        const float lp = fast_lg2(P) * kLn2;
-                                        my_stage[k] = fmaf(v[k], p.scale, -lse) + lp;
+                                        lg[q] = fmaf(fast_lg2(P), kLn2, fmaf(v[k], p.scale, -lse));
                                         v[k] = fast_ex2(fmaf(v[k], c, -mc)) * P;
-                                        sum_w += v[k];
                                     }
+                                    *reinterpret_cast<float4*>(my_stage + 4 * k4) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+                                    sw0 += v[4 * k4]; sw1 += v[4 * k4 + 1];
+                                    sw0 += v[4 * k4 + 2]; sw1 += v[4 * k4 + 3];
                                 }
                             } else {
 #pragma unroll
                                 for (int k4 = 0; k4 < kCW / 4; ++k4) {
                                     const float4 g4 = *reinterpret_cast<const float4*>(gt + j0 + 4 * k4);
-                                    const float gg[4] = {g4.x - u, g4.y - u, g4.z - u, g4.w - u};
+                                    const float dd[4] = {g4.x - us, g4.y - us, g4.z - us, g4.w - us};
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
                                         const int k = 4 * k4 + q;
                                         const bool ok = k < kmax && row_valid;
-                                        float pr = fast_ex2(gg[q] * gg[q] * (kNegInvTwoGammaSq * kLog2e)) * inv_psum;
+                                        float pr = fast_ex2(-dd[q] * dd[q]) * inv_psum;
                                         pr = (ok && pr >= kPriorThreshold) ? pr : 0.0f;
                                         const float P = pr + kPriorEps;
-                                        const float lp = fast_lg2(P) * kLn2;
-                                        my_stage[k] = fmaf(v[k], p.scale, -lse) + lp;
+                                        my_stage[k] = fmaf(fast_lg2(P), kLn2, fmaf(v[k], p.scale, -lse));
                                         const float e = fast_ex2(fmaf(v[k], c, -mc));
                                         v[k] = ok ? e * P : 0.0f;
-                                        sum_w += v[k];
+                                        sw0 += v[k];
                                     }
                                 }
                             }
                         } else if (full) {
+                            const float lse_f = lse - kLogPriorFloor;
 #pragma unroll
-                            for (int k = 0; k < kCW; ++k) {
-                                my_stage[k] = fmaf(v[k], p.scale, -lse) + kLogPriorFloor;
-                                v[k] = fast_ex2(fmaf(v[k], c, -mc)) * kPriorEps;
-                                sum_w += v[k];
+                            for (int k4 = 0; k4 < kCW / 4; ++k4) {
+                                float lg[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int k = 4 * k4 + q;
+                                    lg[q] = fmaf(v[k], p.scale, -lse_f);
+                                    v[k] = fast_ex2(fmaf(v[k], c, -mc)) * kPriorEps;
+                                }
+                                *reinterpret_cast<float4*>(my_stage + 4 * k4) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+                                sw0 += v[4 * k4]; sw1 += v[4 * k4 + 1];
+                                sw0 += v[4 * k4 + 2]; sw1 += v[4 * k4 + 3];
                             }
                         } else {
 #pragma unroll
@@ -522,20 +571,21 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                                 my_stage[k] = fmaf(v[k], p.scale, -lse) + kLogPriorFloor;
                                 const float e = fast_ex2(fmaf(v[k], c, -mc));
                                 v[k] = (k < kmax && row_valid) ? e * kPriorEps : 0.0f;
-                                sum_w += v[k];
+                                sw0 += v[k];
                             }
                         }
                     }
-                    if (ch < nchunks && kmax > 0) tmem_st16(tlane + j0, v);
+                    if (ch < nchunks) tmem_st16(tlane + j0, v);
                     __syncwarp();
-                    store_chunk(stage, g_logits, lane, warp_row0, rows_valid, j0, p.T2max, vec4);
+                    store_chunk_fast(g_logits, j0);
                     __syncwarp();
                 }
 
                 // ---- pass 3: attn_soft = w / sum(w) on valid cells, 0 elsewhere -----------------
-                asm volatile("bar.sync 1, 256;" ::: "memory");              // every thread has read the pass-1 statistics
+                // (.w alone is written: the partner may still be reading x, y, z of the pass-1 exchange)
+                float sum_w = sw0 + sw1;
                 xch[half * kTileM + r_in_tile].w = sum_w;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
                 {
                     const float o = xch[(half ^ 1) * kTileM + r_in_tile].w;
                     sum_w = half == 0 ? sum_w + o : o + sum_w;
@@ -551,17 +601,20 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                         tmem_ld16(tlane + j0, v);
                         if (kmax == kCW) {
 #pragma unroll
-                            for (int k = 0; k < kCW; ++k) my_stage[k] = v[k] * inv_w;
+                            for (int k4 = 0; k4 < kCW / 4; ++k4)
+                                *reinterpret_cast<float4*>(my_stage + 4 * k4) =
+                                    make_float4(v[4 * k4] * inv_w, v[4 * k4 + 1] * inv_w, v[4 * k4 + 2] * inv_w, v[4 * k4 + 3] * inv_w);
                         } else {
 #pragma unroll
                             for (int k = 0; k < kCW; ++k) my_stage[k] = k < kmax ? v[k] * inv_w : 0.0f;
                         }
                     } else {
+                        const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-                        for (int k = 0; k < kCW; ++k) my_stage[k] = 0.0f;
+                        for (int k4 = 0; k4 < kCW / 4; ++k4) *reinterpret_cast<float4*>(my_stage + 4 * k4) = z4;
                     }
                     __syncwarp();
-                    store_chunk(stage, g_soft, lane, warp_row0, rows_valid, j0, p.T2max, vec4);
+                    store_chunk_fast(g_soft, j0);
                     __syncwarp();
                 }
             }

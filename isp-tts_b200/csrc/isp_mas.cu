@@ -762,6 +762,8 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
     long long pc_pre = 0, pc_chain = 0, pc_epi = 0;
     for (int i0 = n - 1; i0 >= 0; i0 -= 32, ++k) {
         // window of this lane's row: bit k <-> column j-31+k  (the path stays within it)
+        long long c_a = 0, c_b = 0, c_c = 0;
+        if (probe_w) c_a = clock64();
         const int qw = j >> 5;
         const uint32_t hi = qw == qw_pref ? w0 : w1;
         const uint32_t lo = qw == qw_pref ? w1 : w2;
@@ -788,7 +790,9 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
             if (++h2 == nconv) { h2 = 0; ++need2; }
         }
         qw_pref = qw;
+        if (probe_w) c_b = clock64();
         emit(pi0, pj, pmyR, pwin, k - 1);                       // (no branch: the first call has no valid row and writes nothing)
+        if (probe_w) c_c = clock64();
         uint32_t myR = 0x80000000u;
         uint32_t R = 0x80000000u;    // one-hot position inside the window; bit 31 <-> column j
 #pragma unroll
@@ -801,6 +805,7 @@ mas_kernel(const __grid_constant__ MasMaps maps, const MasParams p) {
         }
         __syncwarp();                                           // winbuf is rewritten by the next block
         pi0 = i0; pj = j; pmyR = myR; pwin = win;
+        if (probe_w) { const long long c_d = clock64(); pc_pre += c_b - c_a; pc_epi += c_c - c_b; pc_chain += c_d - c_c; }
         j -= __clz(R);                                          // R: position after the block's 32 rows (rows < 1 do not move it)
     }
     emit(pi0, pj, pmyR, pwin, k - 1);

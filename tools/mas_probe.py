@@ -46,7 +46,7 @@ def run(name, ring=0, slots=0, dbg=0, bits_global=0):
     n = int(ml[0])
     print(f"{name} bits_global={bits_global} ring={ring} slots={slots} dbg={dbg}: kernel {min(times):.1f} us (median {np.median(times):.1f}); utterance 0 ({n} x {int(tl[0])}): "
           f"forward {pr[1]-pr[0]} cyc ({(pr[1]-pr[0])/(n+31):.1f}/step), barrier {pr[2]-pr[1]}, "
-          f"backtrack {pr[3]-pr[2]} cyc ({(pr[3]-pr[2])/n:.1f}/row); waiting for logits {pr[4]} cyc, for the neighbour strip {pr[5]} cyc; loader: {pr[7]} cyc of which waiting for free stages {pr[6]}; steady chunks: {pr[9]} x {pr[8]/max(pr[9],1):.0f} cyc; backtrack waiting for converters {pr[10]} cyc, waiting for the zero-fill + writing the ones {pr[3]-pr[14]} cyc", flush=True)
+          f"backtrack {pr[3]-pr[2]} cyc ({(pr[3]-pr[2])/n:.1f}/row); waiting for logits {pr[4]} cyc, for the neighbour strip {pr[5]} cyc; loader: {pr[7]} cyc of which waiting for free stages {pr[6]}; steady chunks: {pr[9]} x {pr[8]/max(pr[9],1):.0f} cyc; backtrack waiting for converters {pr[10]} cyc, per block: windows+prefetch {pr[11]/((n+31)//32):.0f} + outputs {pr[13]/((n+31)//32):.0f} + chain {pr[12]/((n+31)//32):.0f} cyc, waiting for the zero-fill + writing the ones {pr[3]-pr[14]} cyc", flush=True)
 
 
 rings = [int(c) for c in os.environ.get("PROBE_RING", "0").split(",")]
