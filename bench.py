@@ -189,7 +189,7 @@ def run_ours(args, w):
     import torch.distributed as dist
 
     from isp_tts_b200 import synth
-    from isp_tts_b200.alignment import _loglik_cuda
+    from isp_tts_b200.alignment import _loglik_cuda, stage_operands
     from isp_tts_b200.mas import mas_forward
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,10 +243,14 @@ def run_ours(args, w):
         bf = bufs[slot]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(bf["free"])                 # the kernels that read this buffer two steps ago are done
-            bf["q"].copy_(q_host, non_blocking=True)
-            bf["k"].copy_(k_host, non_blocking=True)
             bf["tl"].copy_(tl_host, non_blocking=True)
             bf["ml"].copy_(ml_host, non_blocking=True)
+            if args.e2e_copy == "staged":
+                # ragged staging: only the rows below the lengths cross PCIe, the padding is zero-filled on the device
+                stage_operands(q_host, k_host, bf["tl"], bf["ml"], out_q=bf["q"], out_k=bf["k"])
+            else:
+                bf["q"].copy_(q_host, non_blocking=True)
+                bf["k"].copy_(k_host, non_blocking=True)
             bf["ready"].record(copy_stream)
 
     def step_e2e():
@@ -422,7 +426,10 @@ def run_ours(args, w):
 
     utts = world * B * args.steps
     valid_cells = float((tl * ml).sum()) * world * args.steps
-    h2d = q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size() + 16 * B
+    if args.e2e_copy == "staged":
+        h2d = int((ml.sum() + tl.sum()) * D * q_host.element_size()) + 16 * B
+    else:
+        h2d = q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size() + 16 * B
     out = {
         "metric": METRIC, "value": utts / (total_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -438,7 +445,8 @@ def run_ours(args, w):
         "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
         "e2e": {"value": utts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(dur_host.numel() * 8), "ms_per_step": e2e_ms / args.steps,
-                "api": "isp_loglik_forward + isp_mas_forward through isp_tts_b200 (pinned host Q, K, lengths in; durations out); "
+                "api": ("isp_stage_operands (valid rows only over PCIe) + " if args.e2e_copy == "staged" else "")
+                       + "isp_loglik_forward + isp_mas_forward through isp_tts_b200 (pinned host Q, K, lengths in; durations out); "
                        "the next step's H2D overlaps this step's kernels (two device buffers, one copy stream)"},
         "next_rows": bwd,
         "gpu_launches": 2 * args.steps,
@@ -461,6 +469,8 @@ def main():
     ap.add_argument("--mas-slots", type=int, default=0, help="tuning: utterances per CTA (1|2), 0 = heuristic")
     ap.add_argument("--no-backward", action="store_true", help="skip the f-1 backward measurement that follows the timed steps")
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (cfg5 sweep: 64..4096 with the cfg3 length law); 0 = the workload's own")
+    ap.add_argument("--e2e-copy", default="staged", choices=["staged", "padded"],
+                    help="end-to-end H2D of Q and K: isp_stage_operands (valid rows only) or plain copies of the padded tensors")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (sweeps)")
     args = ap.parse_args()
     from isp_tts_b200 import synth

@@ -127,6 +127,13 @@ int    isp_mas_status(const void* ws, void* stream);
  * Limits: T2max <= ISP_LOGLIK_MAX_T2.
  * Accuracy: within 1e-3 relative of the fp32 reference (tests state the tolerance).
  */
+/* Ragged host -> device staging of Q and K (what the reference does with batch.to(device), tts/utils/trainer.py, for whole
+ * padded tensors).  q_host (B, T1max, D), k_host (B, T2max, D): PINNED host memory, same layout and dtype as the device
+ * tensors; text_len, mel_len: DEVICE int64 (B,), already uploaded on `stream`.  Only rows below the lengths are read
+ * over PCIe; padding rows of q_dev / k_dev are written as zeros (the operand contract of isp_loglik_forward).
+ * D * elem % 16 == 0, all tensors 16 B aligned. */
+int    isp_stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                          int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* stream);
 size_t isp_loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    isp_loglik_forward(const void* Q, const void* K, int dtype,
                           const int64_t* text_len, const int64_t* mel_len,

@@ -17,7 +17,7 @@ ISP_DTYPE_BF16 = 1
 EXPORTS = [
     "isp_version", "isp_last_error", "isp_device_check",
     "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_mas_status",
-    "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_set_option",
+    "isp_stage_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_set_option",
 ]
 
 _lib = None
@@ -55,6 +55,8 @@ def load():
     lib.isp_length_regulate_backward.restype = c_int
     lib.isp_mas_status.argtypes = [vp, vp]
     lib.isp_mas_status.restype = c_int
+    lib.isp_stage_operands.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]
+    lib.isp_stage_operands.restype = c_int
     lib.isp_loglik_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.isp_loglik_workspace_bytes.restype = c_sz
     lib.isp_loglik_forward.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, f32, c_int, vp, vp, vp, c_sz, vp]
@@ -75,7 +77,7 @@ def check(rc: int, what: str):
 
 def set_option(key: str, value: int) -> int:
     rc = load().isp_set_option(key.encode(), int(value))
-    if rc == -1 and key not in ("mas.cols_per_lane", "mas.ring_rows", "mas.slots", "mas.dbg", "mas.bits_global", "mas.no_tma", "loglik.debug_scores"):
+    if rc == -1 and key not in ("mas.cols_per_lane", "mas.ring_rows", "mas.slots", "mas.dbg", "mas.bits_global", "mas.no_tma", "loglik.debug_scores", "stage.ctas"):
         raise IspError(f"unknown option {key!r}")
     return rc
 

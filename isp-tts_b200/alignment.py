@@ -29,7 +29,7 @@ from torch.nn import functional as F
 from . import _lib
 from .mas import mas_forward
 
-__all__ = ["batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
+__all__ = ["stage_operands", "batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
            "Aligner", "AlignerConfig", "AlignerOutput", "loglik_forward"]
 
 MISSING = "???"   # same sentinel string omegaconf uses; the reference's configs compare against it
@@ -177,6 +177,35 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
                                     torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "isp_loglik_forward")
     return soft, logits
+
+
+def stage_operands(q_host: Tensor, k_host: Tensor, text_len: Tensor, mel_len: Tensor,
+                   out_q: Tensor | None = None, out_k: Tensor | None = None):
+    """Host -> device copy of the encoded operands, ragged (isp_stage_operands): only the rows below each utterance's
+    length cross PCIe, the padding rows of the device tensors are written as zeros.  q_host (B, T1, D), k_host (B, T2, D):
+    pinned host tensors (float32 or bfloat16); text_len, mel_len: int64 tensors already on the device.  Enqueued on the
+    current stream.  Returns (q_dev, k_dev), ready for loglik_forward."""
+    dev = text_len.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    if q_host.is_cuda or k_host.is_cuda or not q_host.is_pinned() or not k_host.is_pinned():
+        raise ValueError("q_host and k_host must be pinned host tensors")
+    if q_host.dtype != k_host.dtype or q_host.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("Q and K must both be float32 or both bfloat16")
+    if not q_host.is_contiguous() or not k_host.is_contiguous():
+        raise ValueError("q_host and k_host must be contiguous")
+    B, T1, D = q_host.shape
+    T2 = k_host.shape[1]
+    if out_q is None:
+        out_q = torch.empty((B, T1, D), dtype=q_host.dtype, device=dev)
+    if out_k is None:
+        out_k = torch.empty((B, T2, D), dtype=k_host.dtype, device=dev)
+    dt = _lib.ISP_DTYPE_BF16 if q_host.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+    with torch.cuda.device(dev):
+        rc = lib.isp_stage_operands(q_host.data_ptr(), k_host.data_ptr(), dt, text_len.data_ptr(), mel_len.data_ptr(),
+                                    B, T1, T2, D, out_q.data_ptr(), out_k.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "isp_stage_operands")
+    return out_q, out_k
 
 
 def _scores(q: Tensor, k: Tensor) -> Tensor:

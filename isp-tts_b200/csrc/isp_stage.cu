@@ -1,0 +1,95 @@
+// Host -> device staging of the encoded operands of isp_loglik_forward, ragged: only the rows below each utterance's
+// length cross PCIe; the padding rows of the device tensors are zero-filled here (the operands' contract,
+// tts/models/acoustic/modules/alignment.py:75-76 in the reference: projections are exactly 0 at padded positions).
+//
+// The reference moves whole padded batches with tensor.to(device) (tts/train.py -> trainer: batch.to(device)); with
+// LJSpeech-shaped lengths 40 % of those bytes are padding.  A plain gather kernel reads the pinned host tensors through
+// their device-visible (UVA) addresses: 16 B per lane, eight loads in flight per thread, eight CTAs (PCIe is saturated by any grid from 8 CTAs up: 51 GB/s against 54 GB/s for the DMA of the padded tensors) so that it can
+// run on a copy stream next to the previous step's kernels without taking their SMs.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "isp_internal.h"
+
+namespace isp {
+
+constexpr int kStageUnroll = 8;
+constexpr int kStageThreads = 512;
+
+__global__ void __launch_bounds__(kStageThreads)
+stage_operands_kernel(const uint4* __restrict__ hq, const uint4* __restrict__ hk, const int64_t* __restrict__ text_len,
+                      const int64_t* __restrict__ mel_len, uint4* __restrict__ dq, uint4* __restrict__ dk,
+                      int B, int T1max, int T2max, int vpr /* 16 B vectors per row */) {
+    const long long nq = (long long)B * T1max * vpr, nk = (long long)B * T2max * vpr;
+    const long long total = nq + nk;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * kStageUnroll) {
+        uint4 v[kStageUnroll];
+        bool ok[kStageUnroll];
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const long long idx = base + u * stride;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            ok[u] = false;
+            if (idx < total) {
+                const bool isq = idx < nq;
+                const long long e = isq ? idx : idx - nq;
+                const int T = isq ? T1max : T2max;
+                const long long row = e / vpr;
+                const int b = int(row / T), t = int(row - (long long)b * T);
+                const long long len = isq ? mel_len[b] : text_len[b];
+                ok[u] = true;
+                if (t < len) v[u] = isq ? hq[e] : hk[e];          // PCIe read (zero-copy), only for valid rows
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+            const long long idx = base + u * stride;
+            if (ok[u]) { if (idx < nq) dq[idx] = v[u]; else dk[idx - nq] = v[u]; }
+        }
+    }
+}
+
+static int g_opt_stage_ctas = 0;
+
+int stage_set_option(const char* key, int value, int* prev) {
+    if (!strcmp(key, "stage.ctas")) { *prev = g_opt_stage_ctas; g_opt_stage_ctas = value; return 0; }
+    return -1;
+}
+
+int stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                   int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, cudaStream_t stream) {
+    if (!q_host || !k_host || !text_len || !mel_len || !q_dev || !k_dev) { set_error("isp_stage_operands: null pointer"); return ISP_ERR_INVALID; }
+    if (B <= 0 || T1max <= 0 || T2max <= 0 || D <= 0) { set_error("isp_stage_operands: sizes must be positive"); return ISP_ERR_INVALID; }
+    if (dtype != ISP_DTYPE_F32 && dtype != ISP_DTYPE_BF16) { set_error("isp_stage_operands: dtype must be ISP_DTYPE_F32 or ISP_DTYPE_BF16"); return ISP_ERR_INVALID; }
+    const int elem = dtype == ISP_DTYPE_BF16 ? 2 : 4;
+    if ((size_t(D) * elem) % 16 != 0) { set_error("isp_stage_operands: D * elem = %zu B must be a multiple of 16", size_t(D) * elem); return ISP_ERR_UNSUPPORTED; }
+    if ((reinterpret_cast<uintptr_t>(q_host) | reinterpret_cast<uintptr_t>(k_host) | reinterpret_cast<uintptr_t>(q_dev) | reinterpret_cast<uintptr_t>(k_dev)) & 15) {
+        set_error("isp_stage_operands: all four tensors must be 16 B aligned"); return ISP_ERR_INVALID;
+    }
+    // the host tensors must be visible to the device: pinned (cudaHostAlloc / cudaHostRegister) under unified addressing
+    const void* hp[2] = {q_host, k_host};
+    const void* dev_ptr[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, hp[i]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaPointerGetAttributes(host operand)");
+        if (at.type == cudaMemoryTypeUnregistered || at.devicePointer == nullptr) {
+            set_error("isp_stage_operands: the host operands must be pinned memory (torch .pin_memory() / cudaHostAlloc)");
+            return ISP_ERR_INVALID;
+        }
+        dev_ptr[i] = at.devicePointer;
+    }
+    const int vpr = int(size_t(D) * elem / 16);
+    stage_operands_kernel<<<g_opt_stage_ctas > 0 ? g_opt_stage_ctas : 8, kStageThreads, 0, stream>>>(static_cast<const uint4*>(dev_ptr[0]), static_cast<const uint4*>(dev_ptr[1]),
+                                                           text_len, mel_len, static_cast<uint4*>(q_dev), static_cast<uint4*>(k_dev),
+                                                           B, T1max, T2max, vpr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "stage_operands_kernel launch");
+    return 0;
+}
+
+}  // namespace isp

@@ -205,3 +205,31 @@ def test_backward_bf16_operands(cuda_device):
         grads[dt] = (q.grad.float(), k.grad.float())
     for a, b_ in zip(grads[torch.float32], grads[torch.bfloat16]):
         assert (a - b_).abs().max() <= 0.05 * a.abs().max() + 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stage_operands_ragged_upload(cuda_device, dtype):
+    """isp_stage_operands: rows below the lengths arrive bit-exact, padding rows are zeros on the device whatever the
+    host tensors hold there (the operand contract of alignment.py:75-76), and the log-likelihood of the staged operands
+    equals the one of plainly copied operands."""
+    from isp_tts_b200.alignment import stage_operands
+    B, T1, T2, D = 5, 300, 70, 128
+    tl, ml = synth.lengths(B, T2, T1, True, 77)
+    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, 78)
+    qh = torch.from_numpy(q).to(dtype)
+    kh = torch.from_numpy(k).to(dtype)
+    clean_q, clean_k = qh.clone(), kh.clone()
+    # poison the host padding: it must not reach the device
+    qh[torch.arange(T1)[None, :] >= torch.from_numpy(ml)[:, None]] = 7.0
+    kh[torch.arange(T2)[None, :] >= torch.from_numpy(tl)[:, None]] = -3.0
+    qh, kh = qh.pin_memory(), kh.pin_memory()
+    tlt, mlt = torch.from_numpy(tl).to(cuda_device), torch.from_numpy(ml).to(cuda_device)
+    qd, kd = stage_operands(qh, kh, tlt, mlt)
+    torch.cuda.synchronize()
+    assert torch.equal(qd.cpu(), clean_q) and torch.equal(kd.cpu(), clean_k)
+    s1, l1 = loglik_forward(qd, kd, tlt, mlt)
+    s2, l2 = loglik_forward(clean_q.to(cuda_device), clean_k.to(cuda_device), tlt, mlt)
+    assert torch.equal(s1, s2) and torch.equal(l1, l2)
+    with pytest.raises(ValueError):
+        stage_operands(clean_q, clean_k, tlt, mlt)            # not pinned
