@@ -105,6 +105,10 @@ int    isp_length_regulate(const void* x, const int16_t* path, void* out, int dt
                            int B, int T1max, int T2max, int C, void* stream);
 int    isp_length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
                                     int B, int T1max, int T2max, int C, void* stream);
+/* Per-token average of frame-level features (tts/models/acoustic/modules/temporal_adaptor.py:439-465, `durations` branch):
+ * out[b, c, j] = sum of x[b, c, t] over the token's frames / count of non-zero x among them (0 if none).
+ * x (B, C, T1max) fp32, durations (B, T2max) int64 (the MAS durations), out (B, C, T2max) fp32, all contiguous. */
+int    isp_temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, void* stream);
 /* Reads back (synchronously, after the stream drains) how many utterances had a length
  * outside [1, Tmax] in the last isp_mas_forward that used `ws`.  -1 on error. */
 int    isp_mas_status(const void* ws, void* stream);

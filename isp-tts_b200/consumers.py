@@ -2,6 +2,7 @@
 
 Reference (paths relative to the reference root):
   LengthRegulator.forward(x, durations)     tts/models/acoustic/modules/temporal_adaptor.py:411-436
+  TemporalAverager.forward(x, durations)    tts/models/acoustic/modules/temporal_adaptor.py:439-465
   AttentionBinarizationLoss.forward         tts/models/acoustic/loss.py:97-105   (isp_tts_b200.mas.binarization_loss)
 """
 from __future__ import annotations
@@ -10,7 +11,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["length_regulate", "LengthRegulator"]
+__all__ = ["length_regulate", "LengthRegulator", "temporal_average", "TemporalAverager"]
 
 
 class _LengthRegulate(torch.autograd.Function):
@@ -73,3 +74,33 @@ class LengthRegulator(torch.nn.Module):
             out = out[:, :max_len]
             dec_lens = torch.clamp_max(dec_lens, max_len)
         return out, dec_lens
+
+
+def temporal_average(x: torch.Tensor, durations: torch.Tensor) -> torch.Tensor:
+    """x (B, C, T1) frame-level features, durations (B, T2) -> (B, C, T2): each token's mean over its frames, counting
+    only non-zero values (unvoiced pitch frames are 0), 0 where there is none.  No gradient (the reference feeds targets)."""
+    dev = x.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    if x.dim() != 3 or durations.dim() != 2 or durations.shape[0] != x.shape[0]:
+        raise ValueError("x must be (B, C, T1) and durations (B, T2)")
+    xf = x.detach().float().contiguous()
+    dur = durations.to(device=dev, dtype=torch.int64).contiguous()
+    B, C, T1 = xf.shape
+    T2 = dur.shape[1]
+    out = torch.empty((B, C, T2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.isp_temporal_average(xf.data_ptr(), dur.data_ptr(), out.data_ptr(), B, C, T1, T2,
+                                      torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "isp_temporal_average")
+    return out
+
+
+class TemporalAverager(torch.nn.Module):
+    """Same call as the reference module (temporal_adaptor.py:439-465).  With hard durations the average is one kernel;
+    with a soft `alignment` it is the reference's own matmul (a plain library GEMM, not part of the hot path)."""
+
+    def forward(self, x, durations, alignment=None):
+        if alignment is not None:
+            return x @ alignment / (alignment.sum(dim=1, keepdim=True) + 1e-5)
+        return temporal_average(x, durations)

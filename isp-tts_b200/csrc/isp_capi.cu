@@ -99,6 +99,10 @@ int isp_length_regulate_backward(const float* g, const int64_t* durations, const
     return isp::length_regulate_backward(g, durations, starts, gx, B, T1max, T2max, C, static_cast<cudaStream_t>(stream));
 }
 
+int isp_temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, void* stream) {
+    return isp::temporal_average(x, durations, out, B, C, T1max, T2max, static_cast<cudaStream_t>(stream));
+}
+
 int isp_stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
                        int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* stream) {
     return isp::stage_operands(q_host, k_host, dtype, text_len, mel_len, B, T1max, T2max, D, q_dev, k_dev, static_cast<cudaStream_t>(stream));

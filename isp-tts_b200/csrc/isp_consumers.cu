@@ -144,4 +144,52 @@ int length_regulate_backward(const float* g, const int64_t* durations, const int
 }
 
 
+// Per-token average of a frame-level feature (pitch, energy), tts/models/acoustic/modules/temporal_adaptor.py:439-465
+// (`durations` branch): out[b, c, j] = sum of x[b, c, t] over the token's frames / number of NON-ZERO x among them, 0 if
+// there is none.  The reference takes differences of fp32 running sums over the whole utterance (a dozen kernels and
+// cancellation between two large partial sums); here the token boundaries come from one block scan of the durations and
+// each token's frames are summed directly.
+__global__ void __launch_bounds__(256)
+temporal_average_kernel(const float* __restrict__ x, const int64_t* __restrict__ durations, float* __restrict__ out,
+                        int C, int T1max, int T2max) {
+    extern __shared__ int s_end[];                    // [T2max] inclusive running sum of the durations
+    __shared__ int s_part[256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int64_t* d = durations + size_t(b) * T2max;
+    const int per = (T2max + 255) / 256;              // consecutive tokens per thread
+    const int j0 = tid * per, j1 = min(T2max, j0 + per);
+    int local = 0;
+    for (int j = j0; j < j1; ++j) { const long long v = d[j]; local += int(v < 0 ? 0 : (v > T1max ? T1max : v)); }
+    s_part[tid] = local;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {               // inclusive scan of the per-thread sums
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - local;
+    for (int j = j0; j < j1; ++j) { const long long v = d[j]; run += int(v < 0 ? 0 : (v > T1max ? T1max : v)); s_end[j] = run; }
+    __syncthreads();
+    for (int idx = tid; idx < C * T2max; idx += 256) {
+        const int c = idx / T2max, j = idx - c * T2max;
+        const int t1 = min(s_end[j], T1max), t0 = min(j > 0 ? s_end[j - 1] : 0, t1);
+        const float* xr = x + (size_t(b) * C + c) * T1max;
+        float sum = 0.0f;
+        int cnt = 0;
+        for (int t = t0; t < t1; ++t) { const float v = __ldg(xr + t); sum += v; cnt += v != 0.0f; }
+        out[(size_t(b) * C + c) * T2max + j] = cnt ? sum / float(cnt) : 0.0f;
+    }
+}
+
+int temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, cudaStream_t stream) {
+    if (!x || !durations || !out) { set_error("isp_temporal_average: null pointer"); return ISP_ERR_INVALID; }
+    if (B <= 0 || C <= 0 || T1max <= 0 || T2max <= 0) { set_error("isp_temporal_average: sizes must be positive"); return ISP_ERR_INVALID; }
+    if (T2max > 12288) { set_error("isp_temporal_average: T2max=%d > 12288 tokens", T2max); return ISP_ERR_UNSUPPORTED; }
+    temporal_average_kernel<<<B, 256, size_t(T2max) * sizeof(int), stream>>>(x, durations, out, C, T1max, T2max);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "temporal_average_kernel launch");
+    return 0;
+}
+
 }  // namespace isp

@@ -33,6 +33,7 @@ int    length_regulate(const void* x, const int16_t* path, void* out, int dtype,
 int    length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
                                 int B, int T1max, int T2max, int C, cudaStream_t stream);
 
+int    temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, cudaStream_t stream);
 int    stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
                       int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, cudaStream_t stream);
 

@@ -274,3 +274,36 @@ def test_length_regulator_from_path(cuda_device, dtype):
     (ref * w[:, :ref.shape[1]]).sum().backward()
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     assert torch.allclose(x.grad.float(), x2.grad, rtol=tol, atol=tol * 10)
+
+
+def test_temporal_averager_from_durations(cuda_device):
+    """isp_temporal_average against the reference's running-sum formula (temporal_adaptor.py:447-465), evaluated in
+    float64 so that it is exact, and against the same formula in fp32 within its own cancellation error."""
+    from isp_tts_b200.consumers import TemporalAverager
+    B, T1, T2, C = 6, 400, 90, 2
+    x_l = synth.noise_logits(B, T1, T2, 51)
+    tl, ml = synth.lengths(B, T2, T1, True, 52)
+    mlt = torch.from_numpy(ml).to(cuda_device)
+    _, dur = mas_forward(torch.from_numpy(x_l).to(cuda_device), torch.from_numpy(tl), mlt)
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    x = torch.rand((B, C, T1), device=cuda_device, generator=gen) * 200.0 + 80.0       # pitch-like, Hz
+    x[torch.rand((B, C, T1), device=cuda_device, generator=gen) < 0.3] = 0.0            # unvoiced frames
+    x = x.masked_fill(torch.arange(T1, device=cuda_device)[None, None, :] >= mlt[:, None, None], 0.0)
+    out = TemporalAverager()(x, dur)
+
+    def reference(xx):
+        F = torch.nn.functional
+        ends = torch.cumsum(dur, dim=1).long()
+        starts = F.pad(ends[:, :-1], (1, 0))
+        nz = F.pad(torch.cumsum(xx != 0.0, dim=2), (1, 0))
+        cs = F.pad(torch.cumsum(xx, dim=2), (1, 0))
+        dcs = starts[:, None, :].expand(B, C, T2)
+        dce = ends[:, None, :].expand(B, C, T2)
+        sums = torch.gather(cs, 2, dce) - torch.gather(cs, 2, dcs)
+        n = (torch.gather(nz, 2, dce) - torch.gather(nz, 2, dcs)).to(xx.dtype)
+        return torch.where(n == 0.0, n, sums / n)
+
+    exact = reference(x.double())
+    assert torch.allclose(out.double(), exact, rtol=1e-6, atol=1e-4)
+    assert torch.allclose(out, reference(x), rtol=1e-3, atol=0.5)       # the fp32 running sums reach ~1e5 here
+    assert (out.masked_select(dur[:, None, :].expand(B, C, T2) == 0) == 0).all()
