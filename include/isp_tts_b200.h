@@ -109,6 +109,20 @@ int    isp_length_regulate_backward(const float* g, const int64_t* durations, co
  * out[b, c, j] = sum of x[b, c, t] over the token's frames / count of non-zero x among them (0 if none).
  * x (B, C, T1max) fp32, durations (B, T2max) int64 (the MAS durations), out (B, C, T2max) fp32, all contiguous. */
 int    isp_temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, void* stream);
+/* Forward-sum (CTC) alignment loss, tts/models/acoustic/loss.py:41-79 (AttentionCTCLoss.forward): blank column of value
+ * blank_logprob in front of attn_logits (:67), log_softmax over the T2max + 1 columns (:69), CTC with targets
+ * 1 .. text_len[b] over mel_len[b] frames (:73-78).  isp_ctc_forward writes nll[b] (fp32, natural log; +inf when no
+ * alignment exists, i.e. mel_len[b] < text_len[b]) and keeps the forward variables in `ws`; isp_ctc_backward, called with
+ * the same `ws` afterwards, writes grad_logits[b, i, j] = grad_scale[b] * d nll[b] / d attn_logits[b, i, j] for the whole
+ * (B, T1max, T2max) tensor (zeros past mel_len[b]; all zeros for an utterance whose nll is +inf -- zero_infinity).  The
+ * reference's loss is mean_b(nll[b] / text_len[b]), so grad_scale[b] = upstream / (B * text_len[b]).
+ * attn_logits (B, T1max, T2max) fp32 contiguous; ws 16 B aligned, isp_ctc_workspace_bytes(...) bytes; T2max <= 671. */
+size_t isp_ctc_workspace_bytes(int B, int T1max, int T2max);
+int    isp_ctc_forward(const float* attn_logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                       float blank_logprob, float* nll, void* ws, size_t ws_bytes, void* stream);
+int    isp_ctc_backward(const float* attn_logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                        float blank_logprob, const float* nll, const float* grad_scale, float* grad_logits,
+                        void* ws, size_t ws_bytes, void* stream);
 /* Reads back (synchronously, after the stream drains) how many utterances had a length
  * outside [1, Tmax] in the last isp_mas_forward that used `ws`.  -1 on error. */
 int    isp_mas_status(const void* ws, void* stream);

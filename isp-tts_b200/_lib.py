@@ -16,7 +16,7 @@ ISP_DTYPE_BF16 = 1
 
 EXPORTS = [
     "isp_version", "isp_last_error", "isp_device_check",
-    "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_temporal_average", "isp_mas_status",
+    "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_temporal_average", "isp_ctc_workspace_bytes", "isp_ctc_forward", "isp_ctc_backward", "isp_mas_status",
     "isp_stage_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_set_option",
 ]
 
@@ -55,6 +55,12 @@ def load():
     lib.isp_length_regulate_backward.restype = c_int
     lib.isp_temporal_average.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, vp]
     lib.isp_temporal_average.restype = c_int
+    lib.isp_ctc_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.isp_ctc_workspace_bytes.restype = c_sz
+    lib.isp_ctc_forward.argtypes = [vp, vp, vp, c_int, c_int, c_int, f32, vp, vp, c_sz, vp]
+    lib.isp_ctc_forward.restype = c_int
+    lib.isp_ctc_backward.argtypes = [vp, vp, vp, c_int, c_int, c_int, f32, vp, vp, vp, vp, c_sz, vp]
+    lib.isp_ctc_backward.restype = c_int
     lib.isp_mas_status.argtypes = [vp, vp]
     lib.isp_mas_status.restype = c_int
     lib.isp_stage_operands.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]

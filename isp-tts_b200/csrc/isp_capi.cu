@@ -103,6 +103,20 @@ int isp_temporal_average(const float* x, const int64_t* durations, float* out, i
     return isp::temporal_average(x, durations, out, B, C, T1max, T2max, static_cast<cudaStream_t>(stream));
 }
 
+size_t isp_ctc_workspace_bytes(int B, int T1max, int T2max) { return isp::ctc_workspace_bytes(B, T1max, T2max); }
+
+int isp_ctc_forward(const float* attn_logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                    float blank_logprob, float* nll, void* ws, size_t ws_bytes, void* stream) {
+    return isp::ctc_forward(attn_logits, text_len, mel_len, B, T1max, T2max, blank_logprob, nll, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int isp_ctc_backward(const float* attn_logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                     float blank_logprob, const float* nll, const float* grad_scale, float* grad_logits, void* ws, size_t ws_bytes,
+                     void* stream) {
+    return isp::ctc_backward(attn_logits, text_len, mel_len, B, T1max, T2max, blank_logprob, nll, grad_scale, grad_logits, ws, ws_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int isp_stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
                        int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* stream) {
     return isp::stage_operands(q_host, k_host, dtype, text_len, mel_len, B, T1max, T2max, D, q_dev, k_dev, static_cast<cudaStream_t>(stream));

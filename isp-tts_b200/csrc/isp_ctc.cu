@@ -1,0 +1,393 @@
+// Forward-sum (CTC) alignment loss on the attention log-likelihoods, SURVEY.md section 8 row f-4.
+//
+// Reference (tts/models/acoustic/loss.py:41-79, AttentionCTCLoss.forward): pad a blank column with value blank_logprob in
+// front of attn_logits (:67), log_softmax over the T2max + 1 columns (:69), nn.CTCLoss(zero_infinity=True) with targets
+// 1 .. text_len[b], input_lengths = mel_len, target_lengths = text_len (:73-78; mean over the batch of nll_b / text_len[b]).
+//
+// The same lattice as MAS with (+, x) in place of (max, +): per frame i and token j
+//     blank_j' = pB_i  * (blank_j + label_{j-1})
+//     label_j' = p_ij  * (label_j + blank_j + label_{j-1})          p = softmax over [blank, tokens] of frame i
+// and the likelihood is label_{T2-1} + blank_{T2} after the last frame.  It is a serial chain over the frames, so the kernel
+// is built like the MAS one: ONE WARP PER UTTERANCE, lane l owns G consecutive tokens and, at step t, works on frame t - l
+// (the wavefront is skewed across lanes, so the one value a lane needs from its left neighbour was produced two steps
+// earlier and its shuffle is off the chain; no barrier anywhere).  The recursion runs in the LINEAR domain -- one ex2 per
+// cell for p, then adds and multiplies -- instead of three log-sum-exps per cell: every token's pair {label_j, blank_j} is
+// kept in block floating point (a power-of-two exponent per token and frame, renormalised every step), which holds the
+// hundreds of orders of magnitude between states on and off the path without touching the XU pipe.  (One exponent per LANE
+// is not enough: with mel_len == text_len the one valid path shares a lane with stragglers 2^400 times its size.)
+//
+//   ctc_rownorm_kernel   Z_i = log2(2^blank + sum_j 2^logit_ij) per valid frame (one warp per frame, coalesced)
+//   ctc_alpha_kernel     forward variables (kept in the workspace for the gradient) and nll_b
+//   ctc_beta_grad_kernel backward variables in the mirrored skew and d nll_b / d attn_logits = p_ij - posterior_ij
+//
+// Accuracy: fp32 sums, relative error ~1e-6 per frame at worst; tests state the tolerance against torch's CTC in float64.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "isp_internal.h"
+
+namespace isp {
+
+constexpr float kCtcLog2e = 1.4426950408889634f;
+constexpr float kCtcLn2 = 0.6931471805599453f;
+
+ISP_DEVINL float ctc_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// x * 2^n for any int n (0 on underflow; n <= 127 is the caller's business)
+ISP_DEVINL float ctc_scale(float x, int n) {
+    if (n < -126) return 0.0f;
+    return x * __int_as_float((n + 127) << 23);
+}
+// exponent e of a positive normal float with 2^e <= x < 2^(e+1)
+ISP_DEVINL int ctc_exponent(float x) { return int((__float_as_uint(x) >> 23) & 0xffu) - 127; }
+
+// ---- row normaliser ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ctc_rownorm_kernel(const float* __restrict__ logits, const int64_t* __restrict__ mel_len, float* __restrict__ z2,
+                   int B, int T1max, int T2max, float blank2 /* blank_logprob * log2(e) */) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)B * T1max;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+        const int b = int(row / T1max), i = int(row - (long long)b * T1max);
+        if (i >= mel_len[b]) continue;
+        const float* x = logits + row * T2max;
+        float m = blank2;
+        for (int j = lane; j < T2max; j += 32) m = fmaxf(m, __ldg(x + j) * kCtcLog2e);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = lane == 0 ? ctc_ex2(blank2 - m) : 0.0f;
+        for (int j = lane; j < T2max; j += 32) s += ctc_ex2(fmaf(__ldg(x + j), kCtcLog2e, -m));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) z2[row] = m + log2f(s);
+    }
+}
+
+// ---- forward variables ----------------------------------------------------------------------------------------------
+// Workspace layout: alpha (B, T1max, 32 * G) float2 {label, blank}, exps (B, T1max, 32 * G) int, z2 (B, T1max) float.
+template <int G>
+__global__ void __launch_bounds__(128)
+ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
+                 const int64_t* __restrict__ mel_len, float2* __restrict__ alpha_ws, int* __restrict__ exp_ws,
+                 float* __restrict__ nll, int B, int T1max, int T2max, float blank2) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const long long n64 = mel_len[b], m64 = text_len[b];
+    const int n = int(n64 < 1 ? 1 : (n64 > T1max ? T1max : n64));      // frames
+    const int m = int(m64 < 1 ? 1 : (m64 > T2max ? T2max : m64));      // tokens
+    const int j0 = lane * G;
+    const float* xb = logits + (size_t)b * T1max * T2max;
+    const float* zb = z2 + (size_t)b * T1max;
+    float2* ab = alpha_ws ? alpha_ws + (size_t)b * T1max * (32 * G) : nullptr;
+    int* eb = exp_ws ? exp_ws + (size_t)b * T1max * (32 * G) : nullptr;
+
+    float A[G], Bk[G];                 // label_j, blank_j of the previous frame, times 2^-E[j]
+    int E[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { A[g] = 0.0f; Bk[g] = 0.0f; E[g] = 0; }
+    if (lane == 0) Bk[0] = 1.0f;       // virtual frame -1: all the mass in the blank before token 0
+    // what the right neighbour takes: this lane's last label two steps ago, and its exponent
+    float h1v = 0.0f, h2v = 0.0f;
+    int h1e = 0, h2e = 0;
+    // the row of the lane's next frame, fetched one step ahead
+    float xr[G], zr = 0.0f;
+    auto fetch = [&](int i) {
+        const bool ok = i >= 0 && i < n;
+        zr = ok ? __ldg(zb + i) : 0.0f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) xr[g] = (ok && j0 + g < m) ? __ldg(xb + (size_t)i * T2max + j0 + g) : -CUDART_INF_F;
+    };
+    fetch(-lane);
+    const int steps = n + 31;
+    for (int t = 0; t < steps; ++t) {
+        const int i = t - lane;                                   // this lane's frame
+        const float lv = __shfl_up_sync(0xffffffffu, h2v, 1);
+        const int le = __shfl_up_sync(0xffffffffu, h2e, 1);
+        float p[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) p[g] = ctc_ex2(fmaf(xr[g], kCtcLog2e, -zr));      // 0 for tokens >= m (x = -inf)
+        const float pB = ctc_ex2(blank2 - zr);
+        fetch(i + 1);
+        if (i >= 0 && i < n) {
+#pragma unroll
+            for (int g = G - 1; g >= 0; --g) {
+                // the left neighbour's label of the previous frame, brought to this token's scale
+                float am1 = g > 0 ? A[g - 1] : (lane == 0 ? 0.0f : lv);
+                const int em1 = g > 0 ? E[g - 1] : le;
+                float a = A[g], bk = Bk[g];
+                int e = E[g];
+                if (am1 > 0.0f) {
+                    if (a + bk == 0.0f) e = em1;                  // first mass to reach this token: adopt its scale
+                    const int d = em1 - e;
+                    if (d > 40) {                                 // the neighbour is far above: move to its scale
+                        a = ctc_scale(a, -d);
+                        bk = ctc_scale(bk, -d);
+                        e = em1;
+                    } else {
+                        am1 = ctc_scale(am1, d);
+                    }
+                }
+                const float s = bk + am1;
+                bk = pB * s;
+                a = p[g] * (a + s);
+                const float mx = fmaxf(a, bk);
+                if (mx > 0.0f) {
+                    const int ex = ctc_exponent(mx);
+                    const float sc = __int_as_float((127 - ex) << 23);              // 2^-ex
+                    a *= sc;
+                    bk *= sc;
+                    e += ex;
+                }
+                A[g] = a; Bk[g] = bk; E[g] = e;
+            }
+            if (ab) {
+                float2* dst = ab + (size_t)i * (32 * G) + j0;
+                int* edst = eb + (size_t)i * (32 * G) + j0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) { dst[g] = make_float2(A[g], Bk[g]); edst[g] = E[g]; }
+            }
+        }
+        h2v = h1v; h2e = h1e;
+        h1v = A[G - 1]; h1e = E[G - 1];
+    }
+    // likelihood = label_{m-1} + blank_m after frame n-1 (every lane now holds its frame n-1)
+    const int la = (m - 1) / G, lb = m / G;
+    float va = 0.0f, vb = 0.0f;
+    int ea = 0, ebk = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (lane == la && g == (m - 1) - la * G) { va = A[g]; ea = E[g]; }
+        if (lane == lb && g == m - lb * G) { vb = Bk[g]; ebk = E[g]; }
+    }
+    ea = __shfl_sync(0xffffffffu, ea, la);
+    ebk = __shfl_sync(0xffffffffu, ebk, lb);
+    va = __shfl_sync(0xffffffffu, va, la);
+    vb = __shfl_sync(0xffffffffu, vb, lb);
+    if (lane == 0) {
+        float r = CUDART_INF_F;
+        if (va > 0.0f || vb > 0.0f) {
+            const int em = (va > 0.0f && vb > 0.0f) ? max(ea, ebk) : (va > 0.0f ? ea : ebk);
+            const float s = (va > 0.0f ? ctc_scale(va, ea - em) : 0.0f) + (vb > 0.0f ? ctc_scale(vb, ebk - em) : 0.0f);
+            r = -(log2f(s) + float(em)) * kCtcLn2;
+        }
+        nll[b] = r;                                                 // +inf: no alignment exists (mel_len < text_len)
+    }
+}
+
+// ---- backward variables and the gradient ------------------------------------------------------------------------------
+// With H_i(s) = p_i(s) * beta_i(s) (beta_i(s): probability of frames i+1.. given state s at frame i):
+//     beta_i(label_j) = H_{i+1}(label_j) + H_{i+1}(blank_{j+1}) + H_{i+1}(label_{j+1})
+//     beta_i(blank_j) = H_{i+1}(blank_j) + H_{i+1}(label_j)
+// posterior_ij = alpha_i(label_j) beta_i(label_j) / P, and through the log_softmax d nll / d logit_ij = p_ij - posterior_ij
+// (the posteriors of a frame sum to 1).  Mirrored skew: lane l works on frame n-1 - (t - (31 - l)) and takes its right
+// neighbour's first token from two steps earlier.
+template <int G>
+__global__ void __launch_bounds__(128)
+ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
+                     const int64_t* __restrict__ mel_len, const float2* __restrict__ alpha_ws, const int* __restrict__ exp_ws,
+                     const float* __restrict__ nll, const float* __restrict__ grad_scale, float* __restrict__ grad,
+                     int B, int T1max, int T2max, float blank2) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const long long n64 = mel_len[b], m64 = text_len[b];
+    const int n = int(n64 < 1 ? 1 : (n64 > T1max ? T1max : n64));
+    const int m = int(m64 < 1 ? 1 : (m64 > T2max ? T2max : m64));
+    const int j0 = lane * G;
+    const float* xb = logits + (size_t)b * T1max * T2max;
+    const float* zb = z2 + (size_t)b * T1max;
+    const float2* ab = alpha_ws + (size_t)b * T1max * (32 * G);
+    const int* eb = exp_ws + (size_t)b * T1max * (32 * G);
+    float* gb = grad + (size_t)b * T1max * T2max;
+    const float nl = nll[b];
+    const float gs = grad_scale[b];
+    const bool dead = !(nl < CUDART_INF_F) || gs == 0.0f;           // zero_infinity: no gradient for an impossible alignment
+    // frames past the utterance (all of them when dead) get a zero gradient
+    {
+        const int r0 = dead ? 0 : n;
+        float* z = gb + (size_t)r0 * T2max;
+        const size_t cnt = (size_t)(T1max - r0) * T2max;
+        for (size_t k = lane; k < cnt; k += 32) z[k] = 0.0f;
+        if (dead) return;
+    }
+    const float log2P = -nl * kCtcLog2e;
+
+    float Ha[G], Hb[G];                // H_{i+1}(label_j), H_{i+1}(blank_j), times 2^-F[j]
+    int F[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { Ha[g] = 0.0f; Hb[g] = 0.0f; F[g] = 0; }
+    const int lb = m / G;
+#pragma unroll
+    for (int g = 0; g < G; ++g) if (lane == lb && g == m - lb * G) Hb[g] = 1.0f;      // virtual frame n: blank_m
+    float h1a = 0.0f, h1b = 0.0f, h2a = 0.0f, h2b = 0.0f;          // this lane's first token, one and two steps ago
+    int h1e = 0, h2e = 0;
+    float xr[G], zr = 0.0f;
+    float al[G];
+    int ae[G];
+    auto fetch = [&](int i) {
+        const bool ok = i >= 0 && i < n;
+        zr = ok ? __ldg(zb + i) : 0.0f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            xr[g] = (ok && j0 + g < T2max) ? __ldg(xb + (size_t)i * T2max + j0 + g) : -CUDART_INF_F;
+            al[g] = ok ? __ldg(&ab[(size_t)i * (32 * G) + j0 + g].x) : 0.0f;
+            ae[g] = ok ? __ldg(eb + (size_t)i * (32 * G) + j0 + g) : 0;
+        }
+    };
+    fetch(n - 1 + 31 - lane);
+    h1a = Ha[0]; h1b = Hb[0];
+    h2a = h1a; h2b = h1b;
+    const int steps = n + 31;
+    for (int t = 0; t < steps; ++t) {
+        const int i = n - 1 - t + 31 - lane;
+        const float rav = __shfl_down_sync(0xffffffffu, h2a, 1);
+        const float rbv = __shfl_down_sync(0xffffffffu, h2b, 1);
+        const int re = __shfl_down_sync(0xffffffffu, h2e, 1);
+        float psm[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) psm[g] = ctc_ex2(fmaf(xr[g], kCtcLog2e, -zr));   // softmax over all T2max columns (0 past T2max)
+        const float pB = ctc_ex2(blank2 - zr);
+        float a_cur[G];
+        int e_cur[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) { a_cur[g] = al[g]; e_cur[g] = ae[g]; }
+        fetch(i - 1);
+        if (i >= 0 && i < n) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                // the right neighbour's pair of frame i + 1, brought to this token's scale
+                float na = g + 1 < G ? Ha[g + 1] : (lane == 31 ? 0.0f : rav);
+                float nb = g + 1 < G ? Hb[g + 1] : (lane == 31 ? 0.0f : rbv);
+                const int en = g + 1 < G ? F[g + 1] : re;
+                float ha = Ha[g], hb = Hb[g];
+                int f = F[g];
+                if (na > 0.0f || nb > 0.0f) {
+                    if (ha + hb == 0.0f) f = en;
+                    const int d = en - f;
+                    if (d > 40) {
+                        ha = ctc_scale(ha, -d);
+                        hb = ctc_scale(hb, -d);
+                        f = en;
+                    } else {
+                        na = ctc_scale(na, d);
+                        nb = ctc_scale(nb, d);
+                    }
+                }
+                const float bt_a = ha + nb + na;
+                const float bt_b = hb + ha;
+                // posterior of label_j at frame i: alpha carries 2^e_cur, beta 2^f.  (The exponent is clamped: a token the
+                // forward pass never reached holds zeros under a stale exponent, and 0 * inf is not 0.)
+                const float post = a_cur[g] * bt_a * ctc_ex2(fminf(float(e_cur[g] + f) - log2P, 126.0f));
+                if (j0 + g < T2max) gb[(size_t)i * T2max + j0 + g] = gs * (psm[g] - post);
+                ha = (j0 + g < m ? psm[g] : 0.0f) * bt_a;
+                hb = pB * bt_b;
+                const float mx = fmaxf(ha, hb);
+                if (mx > 0.0f) {
+                    const int ex = ctc_exponent(mx);
+                    const float sc = __int_as_float((127 - ex) << 23);
+                    ha *= sc;
+                    hb *= sc;
+                    f += ex;
+                }
+                Ha[g] = ha; Hb[g] = hb; F[g] = f;
+            }
+        }
+        h2a = h1a; h2b = h1b; h2e = h1e;
+        h1a = Ha[0]; h1b = Hb[0]; h1e = F[0];
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+static int ctc_group(int T2max) { return (T2max + 1 + 31) / 32; }          // tokens per lane (the virtual token T2 included)
+static int ctc_group_padded(int T2max) {
+    const int g = ctc_group(T2max);
+    return g <= 4 ? 4 : (g <= 8 ? 8 : (g <= 12 ? 12 : (g <= 16 ? 16 : (g <= 21 ? 21 : 0))));
+}
+
+size_t ctc_workspace_bytes(int B, int T1max, int T2max) {
+    const int G = ctc_group_padded(T2max);
+    if (B <= 0 || T1max <= 0 || T2max <= 0 || G == 0) return 0;
+    const size_t rows = size_t(B) * T1max;
+    return rows * 32 * G * sizeof(float2) + rows * 32 * G * sizeof(int) + rows * sizeof(float) + 256;
+}
+
+struct CtcWs { float2* alpha; int* exps; float* z2; };
+static CtcWs ctc_carve(void* ws, int B, int T1max, int G) {
+    const size_t rows = size_t(B) * T1max;
+    CtcWs w;
+    w.alpha = static_cast<float2*>(ws);
+    w.exps = reinterpret_cast<int*>(w.alpha + rows * 32 * G);
+    w.z2 = reinterpret_cast<float*>(w.exps + rows * 32 * G);
+    return w;
+}
+
+static int ctc_check(const char* who, const float* logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                     const void* ws, size_t ws_bytes) {
+    if (!logits || !text_len || !mel_len || !ws) { set_error("%s: null pointer", who); return ISP_ERR_INVALID; }
+    if (B <= 0 || T1max <= 0 || T2max <= 0) { set_error("%s: sizes must be positive", who); return ISP_ERR_INVALID; }
+    if (ctc_group_padded(T2max) == 0) { set_error("%s: T2max=%d > 671 text tokens is not covered", who, T2max); return ISP_ERR_UNSUPPORTED; }
+    if (ws_bytes < ctc_workspace_bytes(B, T1max, T2max)) { set_error("%s: workspace of %zu B required, got %zu", who, ctc_workspace_bytes(B, T1max, T2max), ws_bytes); return ISP_ERR_WORKSPACE; }
+    if (reinterpret_cast<uintptr_t>(ws) & 15) { set_error("%s: workspace must be 16 B aligned", who); return ISP_ERR_INVALID; }
+    return 0;
+}
+
+int ctc_forward(const float* logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                float blank_logprob, float* nll, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    int rc = ctc_check("isp_ctc_forward", logits, text_len, mel_len, B, T1max, T2max, ws, ws_bytes);
+    if (rc) return rc;
+    if (!nll) { set_error("isp_ctc_forward: null pointer"); return ISP_ERR_INVALID; }
+    const int G = ctc_group_padded(T2max);
+    const CtcWs w = ctc_carve(ws, B, T1max, G);
+    const float blank2 = blank_logprob * kCtcLog2e;
+    const long long rows = (long long)B * T1max;
+    ctc_rownorm_kernel<<<int(std::min<long long>((rows + 7) / 8, 148LL * 16)), 256, 0, stream>>>(logits, mel_len, w.z2, B, T1max, T2max, blank2);
+    const int grid = (B + 3) / 4;
+#define ISP_CTC_ALPHA(GG) ctc_alpha_kernel<GG><<<grid, 128, 0, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, B, T1max, T2max, blank2)
+    switch (G) {
+        case 4: ISP_CTC_ALPHA(4); break;
+        case 8: ISP_CTC_ALPHA(8); break;
+        case 12: ISP_CTC_ALPHA(12); break;
+        case 16: ISP_CTC_ALPHA(16); break;
+        default: ISP_CTC_ALPHA(21); break;
+    }
+#undef ISP_CTC_ALPHA
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ctc forward launch");
+    return 0;
+}
+
+int ctc_backward(const float* logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                 float blank_logprob, const float* nll, const float* grad_scale, float* grad_logits, void* ws, size_t ws_bytes,
+                 cudaStream_t stream) {
+    int rc = ctc_check("isp_ctc_backward", logits, text_len, mel_len, B, T1max, T2max, ws, ws_bytes);
+    if (rc) return rc;
+    if (!nll || !grad_scale || !grad_logits) { set_error("isp_ctc_backward: null pointer"); return ISP_ERR_INVALID; }
+    const int G = ctc_group_padded(T2max);
+    const CtcWs w = ctc_carve(ws, B, T1max, G);
+    const float blank2 = blank_logprob * kCtcLog2e;
+    const int grid = (B + 3) / 4;
+#define ISP_CTC_BETA(GG) ctc_beta_grad_kernel<GG><<<grid, 128, 0, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, grad_scale, grad_logits, B, T1max, T2max, blank2)
+    switch (G) {
+        case 4: ISP_CTC_BETA(4); break;
+        case 8: ISP_CTC_BETA(8); break;
+        case 12: ISP_CTC_BETA(12); break;
+        case 16: ISP_CTC_BETA(16); break;
+        default: ISP_CTC_BETA(21); break;
+    }
+#undef ISP_CTC_BETA
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ctc backward launch");
+    return 0;
+}
+
+}  // namespace isp
