@@ -388,7 +388,33 @@ def run_ours(args, w):
         bwd["f-3 length regulator"] = {"isp_length_regulate_ms": float(np.mean(t_ours)), "algorithmic_bytes": by_lr,
                                        "gbs": by_lr / float(np.mean(t_ours)) / 1e6, "torch_reference_ms": float(np.mean(t_ref)),
                                        "shape": f"x ({B}, {T2}, {enc_dim}) fp32 -> ({B}, {T1}, {enc_dim})"}
-        del soft_b, logits_b, g_l, g_s, sc, d_s, gq, gk, hard_b, dur_b, path_b, xe, o1, o2
+        del g_l, g_s, sc, d_s, gq, gk, hard_b, dur_b, path_b, xe, o1, o2, soft_b
+        # f-4: forward-sum (CTC) loss and its gradient vs the reference's op sequence on the GPU (loss.py:59-79:
+        # F.pad + log_softmax + transpose + nn.CTCLoss(zero_infinity=True)), same logits
+        from isp_tts_b200.ctc import attention_ctc_loss
+        t_ours, t_ref = [], []
+        tgt = torch.arange(1, T2 + 1, device=dev)[None].expand(B, -1).clone()
+        tgt[tgt > tl_dev[:, None]] = 0
+        for it in range(5):
+            xa = logits_b.detach().clone().requires_grad_(True)
+            xb2 = logits_b.detach().clone().requires_grad_(True)
+            ev[0].record()
+            la = attention_ctc_loss(xa, tl_dev, ml_dev)
+            la.backward()
+            ev[1].record()
+            lp = torch.nn.functional.log_softmax(torch.nn.functional.pad(xb2, (1, 0), value=-1.0), dim=2).transpose(0, 1)
+            lb2 = torch.nn.functional.ctc_loss(lp, tgt, ml_dev, tl_dev, blank=0, reduction="mean", zero_infinity=True)
+            lb2.backward()
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                t_ours.append(ev[0].elapsed_time(ev[1])); t_ref.append(ev[1].elapsed_time(ev[2]))
+        if abs(float(la) - float(lb2)) > 1e-4 * max(1.0, abs(float(lb2))):
+            raise RuntimeError("forward-sum loss differs from torch's CTC: %r vs %r" % (float(la), float(lb2)))
+        gerr = float((xa.grad - xb2.grad).abs().max() / xb2.grad.abs().max())
+        bwd["f-4 forward-sum (CTC) loss"] = {"isp_ctc_forward_backward_ms": float(np.mean(t_ours)), "torch_reference_sequence_ms": float(np.mean(t_ref)),
+                                             "value": float(la), "grad_max_rel_diff_vs_torch_fp32": gerr}
+        del logits_b, xa, xb2, lp
 
     if rank != 0:
         if world > 1:

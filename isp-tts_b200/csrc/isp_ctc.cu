@@ -46,8 +46,25 @@ ISP_DEVINL float ctc_scale(float x, int n) {
     if (n < -126) return 0.0f;
     return x * __int_as_float((n + 127) << 23);
 }
+// 2^k for k <= 127, 0 for k < -126 (no branch: the bodies below are straight-line code, a warp's lanes diverge on every test)
+ISP_DEVINL float ctc_pow2(int k) { return __int_as_float((max(k, -127) + 127) << 23); }
 // exponent e of a positive normal float with 2^e <= x < 2^(e+1)
 ISP_DEVINL int ctc_exponent(float x) { return int((__float_as_uint(x) >> 23) & 0xffu) - 127; }
+
+// Per-lane ring of prefetched rows in shared memory: a lane copies the words of its own frames with 4 B async copies and
+// reads only what it copied itself, so cp.async.wait_group is all the synchronisation there is.  Depth 8: a step takes a
+// few hundred cycles, a load from HBM under load well over a thousand.  A lane's G logits of a frame are 16 B vectors when
+// T2max % 4 == 0 (G is a multiple of 4); the forward variables are kept in the workspace in the order the forward pass
+// produces them -- (step, lane, token), "skewed" -- and the backward pass at its step s wants exactly the forward step
+// n + 30 - s for every lane, so both passes touch them with coalesced 16 B vectors.
+constexpr int kCtcDepth = 8;
+ISP_DEVINL void ctc_cp4(float* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+ISP_DEVINL void ctc_cp16(float* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+ISP_DEVINL int ctc_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ---- row normaliser ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -73,11 +90,11 @@ ctc_rownorm_kernel(const float* __restrict__ logits, const int64_t* __restrict__
 }
 
 // ---- forward variables ----------------------------------------------------------------------------------------------
-// Workspace layout: alpha (B, T1max, 32 * G) float2 {label, blank}, exps (B, T1max, 32 * G) int, z2 (B, T1max) float.
+// Workspace layout: alpha (B, T1max + 31, 32, G) float (labels, by forward step), exps likewise int, z2 (B, T1max) float.
 template <int G>
 __global__ void __launch_bounds__(128)
 ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
-                 const int64_t* __restrict__ mel_len, float2* __restrict__ alpha_ws, int* __restrict__ exp_ws,
+                 const int64_t* __restrict__ mel_len, float* __restrict__ alpha_ws, int* __restrict__ exp_ws,
                  float* __restrict__ nll, int B, int T1max, int T2max, float blank2) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -88,8 +105,8 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
     const int j0 = lane * G;
     const float* xb = logits + (size_t)b * T1max * T2max;
     const float* zb = z2 + (size_t)b * T1max;
-    float2* ab = alpha_ws ? alpha_ws + (size_t)b * T1max * (32 * G) : nullptr;
-    int* eb = exp_ws ? exp_ws + (size_t)b * T1max * (32 * G) : nullptr;
+    float* ab = alpha_ws ? alpha_ws + (size_t)b * (T1max + 31) * (32 * G) : nullptr;      // [step][lane][G]
+    int* eb = exp_ws ? exp_ws + (size_t)b * (T1max + 31) * (32 * G) : nullptr;
 
     float A[G], Bk[G];                 // label_j, blank_j of the previous frame, times 2^-E[j]
     int E[G];
@@ -99,25 +116,39 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
     // what the right neighbour takes: this lane's last label two steps ago, and its exponent
     float h1v = 0.0f, h2v = 0.0f;
     int h1e = 0, h2e = 0;
-    // the row of the lane's next frame, fetched one step ahead
-    float xr[G], zr = 0.0f;
-    auto fetch = [&](int i) {
-        const bool ok = i >= 0 && i < n;
-        zr = ok ? __ldg(zb + i) : 0.0f;
+    // the rows of the lane's next frames, kCtcDepth - 1 steps ahead (addresses clamped; masks applied when the row is used)
+    extern __shared__ float ctc_smem[];
+    constexpr int W = G + 4;                                        // words per lane and stage: G logits, z (16 B slots)
+    float* ring = ctc_smem + (size_t)(threadIdx.x >> 5) * kCtcDepth * 32 * W + lane * W;
+    const bool vec = (T2max & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+    auto issue = [&](int step) {
+        const int i = ctc_clampi(step - lane, 0, n - 1);
+        float* dst = ring + (step & (kCtcDepth - 1)) * 32 * W;
+        const float* src = xb + (size_t)i * T2max;
+        if (vec) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) xr[g] = (ok && j0 + g < m) ? __ldg(xb + (size_t)i * T2max + j0 + g) : -CUDART_INF_F;
+            for (int g = 0; g < G; g += 4) ctc_cp16(dst + g, src + min(j0 + g, T2max - 4));
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) ctc_cp4(dst + g, src + min(j0 + g, T2max - 1));
+        }
+        ctc_cp4(dst + G, zb + i);
+        cp_async_commit();
     };
-    fetch(-lane);
+    for (int st = 0; st < kCtcDepth - 1; ++st) issue(st);
     const int steps = n + 31;
     for (int t = 0; t < steps; ++t) {
         const int i = t - lane;                                   // this lane's frame
         const float lv = __shfl_up_sync(0xffffffffu, h2v, 1);
         const int le = __shfl_up_sync(0xffffffffu, h2e, 1);
+        issue(t + kCtcDepth - 1);
+        cp_async_wait_pending(kCtcDepth - 1);                     // the copies of step t have landed
+        const float* row = ring + (t & (kCtcDepth - 1)) * 32 * W;
+        const float zr = row[G];
         float p[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) p[g] = ctc_ex2(fmaf(xr[g], kCtcLog2e, -zr));      // 0 for tokens >= m (x = -inf)
+        for (int g = 0; g < G; ++g) p[g] = j0 + g < m ? ctc_ex2(fmaf(row[g], kCtcLog2e, -zr)) : 0.0f;
         const float pB = ctc_ex2(blank2 - zr);
-        fetch(i + 1);
         if (i >= 0 && i < n) {
 #pragma unroll
             for (int g = G - 1; g >= 0; --g) {
@@ -126,35 +157,33 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
                 const int em1 = g > 0 ? E[g - 1] : le;
                 float a = A[g], bk = Bk[g];
                 int e = E[g];
-                if (am1 > 0.0f) {
-                    if (a + bk == 0.0f) e = em1;                  // first mass to reach this token: adopt its scale
-                    const int d = em1 - e;
-                    if (d > 40) {                                 // the neighbour is far above: move to its scale
-                        a = ctc_scale(a, -d);
-                        bk = ctc_scale(bk, -d);
-                        e = em1;
-                    } else {
-                        am1 = ctc_scale(am1, d);
-                    }
-                }
-                const float s = bk + am1;
+                const bool inc = am1 > 0.0f;
+                e = (inc && a + bk == 0.0f) ? em1 : e;            // first mass to reach this token: adopt its scale
+                const int d = min(em1 - e, 41);
+                const bool big = inc && d > 40;                   // the neighbour is far above: move to its scale
+                const float f_own = big ? ctc_pow2(e - em1) : 1.0f;
+                const float f_in = big ? 1.0f : ctc_pow2(d);
+                e = big ? em1 : e;
+                const float s = fmaf(bk, f_own, am1 * f_in);
                 bk = pB * s;
-                a = p[g] * (a + s);
-                const float mx = fmaxf(a, bk);
-                if (mx > 0.0f) {
-                    const int ex = ctc_exponent(mx);
-                    const float sc = __int_as_float((127 - ex) << 23);              // 2^-ex
-                    a *= sc;
-                    bk *= sc;
-                    e += ex;
-                }
+                a = p[g] * fmaf(a, f_own, s);
+                // renormalise the pair (a zero pair gets a meaningless exponent; it is adopted away above)
+                const int ex = ctc_exponent(fmaxf(a, bk));
+                const float sc = __int_as_float((127 - ex) << 23);                  // 2^-ex
+                a *= sc;
+                bk *= sc;
+                e += ex;
                 A[g] = a; Bk[g] = bk; E[g] = e;
             }
             if (ab) {
-                float2* dst = ab + (size_t)i * (32 * G) + j0;
-                int* edst = eb + (size_t)i * (32 * G) + j0;
+                // the gradient needs the labels' forward variables only; skewed order, 16 B vectors
+                float4* dst = reinterpret_cast<float4*>(ab + (size_t)t * (32 * G) + j0);
+                int4* edst = reinterpret_cast<int4*>(eb + (size_t)t * (32 * G) + j0);
 #pragma unroll
-                for (int g = 0; g < G; ++g) { dst[g] = make_float2(A[g], Bk[g]); edst[g] = E[g]; }
+                for (int g = 0; g < G; g += 4) {
+                    dst[g >> 2] = make_float4(A[g], A[g + 1], A[g + 2], A[g + 3]);
+                    edst[g >> 2] = make_int4(E[g], E[g + 1], E[g + 2], E[g + 3]);
+                }
             }
         }
         h2v = h1v; h2e = h1e;
@@ -194,7 +223,7 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
 template <int G>
 __global__ void __launch_bounds__(128)
 ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
-                     const int64_t* __restrict__ mel_len, const float2* __restrict__ alpha_ws, const int* __restrict__ exp_ws,
+                     const int64_t* __restrict__ mel_len, const float* __restrict__ alpha_ws, const int* __restrict__ exp_ws,
                      const float* __restrict__ nll, const float* __restrict__ grad_scale, float* __restrict__ grad,
                      int B, int T1max, int T2max, float blank2) {
     const int lane = threadIdx.x & 31;
@@ -206,8 +235,8 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
     const int j0 = lane * G;
     const float* xb = logits + (size_t)b * T1max * T2max;
     const float* zb = z2 + (size_t)b * T1max;
-    const float2* ab = alpha_ws + (size_t)b * T1max * (32 * G);
-    const int* eb = exp_ws + (size_t)b * T1max * (32 * G);
+    const float* ab = alpha_ws + (size_t)b * (T1max + 31) * (32 * G);                     // [forward step][lane][G]
+    const int* eb = exp_ws + (size_t)b * (T1max + 31) * (32 * G);
     float* gb = grad + (size_t)b * T1max * T2max;
     const float nl = nll[b];
     const float gs = grad_scale[b];
@@ -231,20 +260,33 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
     for (int g = 0; g < G; ++g) if (lane == lb && g == m - lb * G) Hb[g] = 1.0f;      // virtual frame n: blank_m
     float h1a = 0.0f, h1b = 0.0f, h2a = 0.0f, h2b = 0.0f;          // this lane's first token, one and two steps ago
     int h1e = 0, h2e = 0;
-    float xr[G], zr = 0.0f;
-    float al[G];
-    int ae[G];
-    auto fetch = [&](int i) {
-        const bool ok = i >= 0 && i < n;
-        zr = ok ? __ldg(zb + i) : 0.0f;
+    extern __shared__ float ctc_smem[];
+    constexpr int W = 3 * G + 4;                                    // logits, alpha labels, alpha exponents, z (16 B slots)
+    float* ring = ctc_smem + (size_t)(threadIdx.x >> 5) * kCtcDepth * 32 * W + lane * W;
+    const bool vec = (T2max & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+    auto issue = [&](int step) {
+        const int i = ctc_clampi(n - 1 - step + 31 - lane, 0, n - 1);
+        const int ta = ctc_clampi(n + 30 - step, 0, n + 30);          // the forward step that produced this step's frames
+        float* dst = ring + (step & (kCtcDepth - 1)) * 32 * W;
+        const float* src = xb + (size_t)i * T2max;
+        const float* asrc = ab + (size_t)ta * (32 * G) + j0;
+        const int* esrc = eb + (size_t)ta * (32 * G) + j0;
+        if (vec) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            xr[g] = (ok && j0 + g < T2max) ? __ldg(xb + (size_t)i * T2max + j0 + g) : -CUDART_INF_F;
-            al[g] = ok ? __ldg(&ab[(size_t)i * (32 * G) + j0 + g].x) : 0.0f;
-            ae[g] = ok ? __ldg(eb + (size_t)i * (32 * G) + j0 + g) : 0;
+            for (int g = 0; g < G; g += 4) ctc_cp16(dst + g, src + min(j0 + g, T2max - 4));
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) ctc_cp4(dst + g, src + min(j0 + g, T2max - 1));
         }
+#pragma unroll
+        for (int g = 0; g < G; g += 4) {
+            ctc_cp16(dst + G + g, asrc + g);
+            ctc_cp16(dst + 2 * G + g, esrc + g);
+        }
+        ctc_cp4(dst + 3 * G, zb + i);
+        cp_async_commit();
     };
-    fetch(n - 1 + 31 - lane);
+    for (int st = 0; st < kCtcDepth - 1; ++st) issue(st);
     h1a = Ha[0]; h1b = Hb[0];
     h2a = h1a; h2b = h1b;
     const int steps = n + 31;
@@ -253,16 +295,21 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
         const float rav = __shfl_down_sync(0xffffffffu, h2a, 1);
         const float rbv = __shfl_down_sync(0xffffffffu, h2b, 1);
         const int re = __shfl_down_sync(0xffffffffu, h2e, 1);
-        float psm[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) psm[g] = ctc_ex2(fmaf(xr[g], kCtcLog2e, -zr));   // softmax over all T2max columns (0 past T2max)
-        const float pB = ctc_ex2(blank2 - zr);
-        float a_cur[G];
+        issue(t + kCtcDepth - 1);
+        cp_async_wait_pending(kCtcDepth - 1);                     // the copies of step t have landed
+        const float* row = ring + (t & (kCtcDepth - 1)) * 32 * W;
+        const float zr = row[3 * G];
+        float psm[G], a_cur[G];
         int e_cur[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) { a_cur[g] = al[g]; e_cur[g] = ae[g]; }
-        fetch(i - 1);
+        for (int g = 0; g < G; ++g) {
+            psm[g] = j0 + g < T2max ? ctc_ex2(fmaf(row[g], kCtcLog2e, -zr)) : 0.0f;   // softmax over all T2max columns
+            a_cur[g] = row[G + g];
+            e_cur[g] = __float_as_int(row[2 * G + g]);
+        }
+        const float pB = ctc_ex2(blank2 - zr);
         if (i >= 0 && i < n) {
+            float gr[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 // the right neighbour's pair of frame i + 1, brought to this token's scale
@@ -271,35 +318,40 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
                 const int en = g + 1 < G ? F[g + 1] : re;
                 float ha = Ha[g], hb = Hb[g];
                 int f = F[g];
-                if (na > 0.0f || nb > 0.0f) {
-                    if (ha + hb == 0.0f) f = en;
-                    const int d = en - f;
-                    if (d > 40) {
-                        ha = ctc_scale(ha, -d);
-                        hb = ctc_scale(hb, -d);
-                        f = en;
-                    } else {
-                        na = ctc_scale(na, d);
-                        nb = ctc_scale(nb, d);
-                    }
-                }
+                const bool inc = na > 0.0f || nb > 0.0f;
+                f = (inc && ha + hb == 0.0f) ? en : f;
+                const int d = min(en - f, 41);
+                const bool big = inc && d > 40;
+                const float f_own = big ? ctc_pow2(f - en) : 1.0f;
+                const float f_in = big ? 1.0f : ctc_pow2(d);
+                f = big ? en : f;
+                ha *= f_own;
+                hb *= f_own;
+                na *= f_in;
+                nb *= f_in;
                 const float bt_a = ha + nb + na;
                 const float bt_b = hb + ha;
                 // posterior of label_j at frame i: alpha carries 2^e_cur, beta 2^f.  (The exponent is clamped: a token the
                 // forward pass never reached holds zeros under a stale exponent, and 0 * inf is not 0.)
                 const float post = a_cur[g] * bt_a * ctc_ex2(fminf(float(e_cur[g] + f) - log2P, 126.0f));
-                if (j0 + g < T2max) gb[(size_t)i * T2max + j0 + g] = gs * (psm[g] - post);
+                gr[g] = gs * (psm[g] - post);
                 ha = (j0 + g < m ? psm[g] : 0.0f) * bt_a;
                 hb = pB * bt_b;
-                const float mx = fmaxf(ha, hb);
-                if (mx > 0.0f) {
-                    const int ex = ctc_exponent(mx);
-                    const float sc = __int_as_float((127 - ex) << 23);
-                    ha *= sc;
-                    hb *= sc;
-                    f += ex;
-                }
+                const int ex = ctc_exponent(fmaxf(ha, hb));
+                const float sc = __int_as_float((127 - ex) << 23);
+                ha *= sc;
+                hb *= sc;
+                f += ex;
                 Ha[g] = ha; Hb[g] = hb; F[g] = f;
+            }
+            float* grow = gb + (size_t)i * T2max + j0;
+            if (vec && (reinterpret_cast<uintptr_t>(grad) & 15) == 0) {
+#pragma unroll
+                for (int g = 0; g < G; g += 4)
+                    if (j0 + g < T2max) *reinterpret_cast<float4*>(grow + g) = make_float4(gr[g], gr[g + 1], gr[g + 2], gr[g + 3]);
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; ++g) if (j0 + g < T2max) grow[g] = gr[g];
             }
         }
         h2a = h1a; h2b = h1b; h2e = h1e;
@@ -311,23 +363,25 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
 static int ctc_group(int T2max) { return (T2max + 1 + 31) / 32; }          // tokens per lane (the virtual token T2 included)
 static int ctc_group_padded(int T2max) {
     const int g = ctc_group(T2max);
-    return g <= 4 ? 4 : (g <= 8 ? 8 : (g <= 12 ? 12 : (g <= 16 ? 16 : (g <= 21 ? 21 : 0))));
+    return g <= 4 ? 4 : (g <= 8 ? 8 : (g <= 12 ? 12 : (g <= 16 ? 16 : 0)));
 }
+
+static int ctc_warps_per_cta(int G) { return G <= 8 ? 4 : 2; }     // the backward ring is 1 KB * (3G + 4) per warp
 
 size_t ctc_workspace_bytes(int B, int T1max, int T2max) {
     const int G = ctc_group_padded(T2max);
     if (B <= 0 || T1max <= 0 || T2max <= 0 || G == 0) return 0;
-    const size_t rows = size_t(B) * T1max;
-    return rows * 32 * G * sizeof(float2) + rows * 32 * G * sizeof(int) + rows * sizeof(float) + 256;
+    const size_t rows = size_t(B) * T1max, srows = size_t(B) * (T1max + 31);
+    return srows * 32 * G * sizeof(float) + srows * 32 * G * sizeof(int) + rows * sizeof(float) + 256;
 }
 
-struct CtcWs { float2* alpha; int* exps; float* z2; };
+struct CtcWs { float* alpha; int* exps; float* z2; };
 static CtcWs ctc_carve(void* ws, int B, int T1max, int G) {
-    const size_t rows = size_t(B) * T1max;
+    const size_t srows = size_t(B) * (T1max + 31);
     CtcWs w;
-    w.alpha = static_cast<float2*>(ws);
-    w.exps = reinterpret_cast<int*>(w.alpha + rows * 32 * G);
-    w.z2 = reinterpret_cast<float*>(w.exps + rows * 32 * G);
+    w.alpha = static_cast<float*>(ws);
+    w.exps = reinterpret_cast<int*>(w.alpha + srows * 32 * G);
+    w.z2 = reinterpret_cast<float*>(w.exps + srows * 32 * G);
     return w;
 }
 
@@ -335,7 +389,7 @@ static int ctc_check(const char* who, const float* logits, const int64_t* text_l
                      const void* ws, size_t ws_bytes) {
     if (!logits || !text_len || !mel_len || !ws) { set_error("%s: null pointer", who); return ISP_ERR_INVALID; }
     if (B <= 0 || T1max <= 0 || T2max <= 0) { set_error("%s: sizes must be positive", who); return ISP_ERR_INVALID; }
-    if (ctc_group_padded(T2max) == 0) { set_error("%s: T2max=%d > 671 text tokens is not covered", who, T2max); return ISP_ERR_UNSUPPORTED; }
+    if (ctc_group_padded(T2max) == 0) { set_error("%s: T2max=%d > 511 text tokens is not covered", who, T2max); return ISP_ERR_UNSUPPORTED; }
     if (ws_bytes < ctc_workspace_bytes(B, T1max, T2max)) { set_error("%s: workspace of %zu B required, got %zu", who, ctc_workspace_bytes(B, T1max, T2max), ws_bytes); return ISP_ERR_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(ws) & 15) { set_error("%s: workspace must be 16 B aligned", who); return ISP_ERR_INVALID; }
     return 0;
@@ -351,14 +405,20 @@ int ctc_forward(const float* logits, const int64_t* text_len, const int64_t* mel
     const float blank2 = blank_logprob * kCtcLog2e;
     const long long rows = (long long)B * T1max;
     ctc_rownorm_kernel<<<int(std::min<long long>((rows + 7) / 8, 148LL * 16)), 256, 0, stream>>>(logits, mel_len, w.z2, B, T1max, T2max, blank2);
-    const int grid = (B + 3) / 4;
-#define ISP_CTC_ALPHA(GG) ctc_alpha_kernel<GG><<<grid, 128, 0, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, B, T1max, T2max, blank2)
+    const int wpc = ctc_warps_per_cta(G);
+    const int grid = (B + wpc - 1) / wpc;
+#define ISP_CTC_ALPHA(GG)                                                                                                   \
+    {                                                                                                                        \
+        const size_t sm = size_t(wpc) * kCtcDepth * 32 * (GG + 4) * sizeof(float);                                         \
+        cudaError_t ea = cudaFuncSetAttribute(ctc_alpha_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));    \
+        if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(ctc_alpha_kernel)");                               \
+        ctc_alpha_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, B, T1max, T2max, blank2); \
+    }
     switch (G) {
-        case 4: ISP_CTC_ALPHA(4); break;
-        case 8: ISP_CTC_ALPHA(8); break;
-        case 12: ISP_CTC_ALPHA(12); break;
-        case 16: ISP_CTC_ALPHA(16); break;
-        default: ISP_CTC_ALPHA(21); break;
+        case 4: ISP_CTC_ALPHA(4) break;
+        case 8: ISP_CTC_ALPHA(8) break;
+        case 12: ISP_CTC_ALPHA(12) break;
+        default: ISP_CTC_ALPHA(16) break;
     }
 #undef ISP_CTC_ALPHA
     cudaError_t e = cudaGetLastError();
@@ -375,14 +435,21 @@ int ctc_backward(const float* logits, const int64_t* text_len, const int64_t* me
     const int G = ctc_group_padded(T2max);
     const CtcWs w = ctc_carve(ws, B, T1max, G);
     const float blank2 = blank_logprob * kCtcLog2e;
-    const int grid = (B + 3) / 4;
-#define ISP_CTC_BETA(GG) ctc_beta_grad_kernel<GG><<<grid, 128, 0, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, grad_scale, grad_logits, B, T1max, T2max, blank2)
+    const int wpc = ctc_warps_per_cta(G);
+    const int grid = (B + wpc - 1) / wpc;
+#define ISP_CTC_BETA(GG)                                                                                                    \
+    {                                                                                                                        \
+        const size_t sm = size_t(wpc) * kCtcDepth * 32 * (3 * GG + 4) * sizeof(float);                                     \
+        cudaError_t ea = cudaFuncSetAttribute(ctc_beta_grad_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)); \
+        if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(ctc_beta_grad_kernel)");                            \
+        ctc_beta_grad_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, grad_scale, \
+                                                                 grad_logits, B, T1max, T2max, blank2);                       \
+    }
     switch (G) {
-        case 4: ISP_CTC_BETA(4); break;
-        case 8: ISP_CTC_BETA(8); break;
-        case 12: ISP_CTC_BETA(12); break;
-        case 16: ISP_CTC_BETA(16); break;
-        default: ISP_CTC_BETA(21); break;
+        case 4: ISP_CTC_BETA(4) break;
+        case 8: ISP_CTC_BETA(8) break;
+        case 12: ISP_CTC_BETA(12) break;
+        default: ISP_CTC_BETA(16) break;
     }
 #undef ISP_CTC_BETA
     cudaError_t e = cudaGetLastError();
