@@ -409,11 +409,11 @@ def run_ours(args, w):
             torch.cuda.synchronize()
             if it >= 2:
                 t_ours.append(ev[0].elapsed_time(ev[1])); t_ref.append(ev[1].elapsed_time(ev[2]))
-        if abs(float(la) - float(lb2)) > 1e-4 * max(1.0, abs(float(lb2))):
-            raise RuntimeError("forward-sum loss differs from torch's CTC: %r vs %r" % (float(la), float(lb2)))
+        if abs(la.item() - lb2.item()) > 1e-4 * max(1.0, abs(lb2.item())):
+            raise RuntimeError("forward-sum loss differs from torch CTC: %r vs %r" % (la.item(), lb2.item()))
         gerr = float((xa.grad - xb2.grad).abs().max() / xb2.grad.abs().max())
         bwd["f-4 forward-sum (CTC) loss"] = {"isp_ctc_forward_backward_ms": float(np.mean(t_ours)), "torch_reference_sequence_ms": float(np.mean(t_ref)),
-                                             "value": float(la), "grad_max_rel_diff_vs_torch_fp32": gerr}
+                                             "value": la.item(), "grad_max_rel_diff_vs_torch_fp32": gerr}
         del logits_b, xa, xb2, lp
 
     if rank != 0:
