@@ -10,17 +10,19 @@
 // and the likelihood is label_{T2-1} + blank_{T2} after the last frame.  It is a serial chain over the frames, so the kernel
 // is built like the MAS one: ONE WARP PER UTTERANCE, lane l owns G consecutive tokens and, at step t, works on frame t - l
 // (the wavefront is skewed across lanes, so the one value a lane needs from its left neighbour was produced two steps
-// earlier and its shuffle is off the chain; no barrier anywhere).  The recursion runs in the LINEAR domain -- one ex2 per
-// cell for p, then adds and multiplies -- instead of three log-sum-exps per cell: every token's pair {label_j, blank_j} is
-// kept in block floating point (a power-of-two exponent per token and frame, renormalised every step), which holds the
-// hundreds of orders of magnitude between states on and off the path without touching the XU pipe.  (One exponent per LANE
-// is not enough: with mel_len == text_len the one valid path shares a lane with stragglers 2^400 times its size.)
+// earlier and its shuffle is off the chain; no barrier anywhere).  The variables are base-2 logarithms.  With
+// lse(x, y) = max(x, y) + log2(1 + 2^-|x - y|) the blank needs one lse and the label one more on top of it (the inner sum
+// is shared), i.e. 2 ex2 + 2 lg2 per cell and a dozen FMA-pipe instructions.  (A linear-domain recursion in block floating
+// point -- one ex2 per cell, a power-of-two exponent per token -- was built first and measured 2x slower: its integer
+// exponent bookkeeping runs on the half-rate ALU pipe, 40 instructions per cell.)  Unreachable states hold -1e30 instead
+// of -inf so that no difference is ever NaN.
 //
 //   ctc_rownorm_kernel   Z_i = log2(2^blank + sum_j 2^logit_ij) per valid frame (one warp per frame, coalesced)
 //   ctc_alpha_kernel     forward variables (kept in the workspace for the gradient) and nll_b
 //   ctc_beta_grad_kernel backward variables in the mirrored skew and d nll_b / d attn_logits = p_ij - posterior_ij
 //
-// Accuracy: fp32 sums, relative error ~1e-6 per frame at worst; tests state the tolerance against torch's CTC in float64.
+// Accuracy: fp32 with ex2.approx / lg2.approx (abs error ~2^-22 per lse in log2 units); tests state the tolerance against
+// torch's CTC in float64.
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -41,15 +43,14 @@ ISP_DEVINL float ctc_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// x * 2^n for any int n (0 on underflow; n <= 127 is the caller's business)
-ISP_DEVINL float ctc_scale(float x, int n) {
-    if (n < -126) return 0.0f;
-    return x * __int_as_float((n + 127) << 23);
+ISP_DEVINL float ctc_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-// 2^k for k <= 127, 0 for k < -126 (no branch: the bodies below are straight-line code, a warp's lanes diverge on every test)
-ISP_DEVINL float ctc_pow2(int k) { return __int_as_float((max(k, -127) + 127) << 23); }
-// exponent e of a positive normal float with 2^e <= x < 2^(e+1)
-ISP_DEVINL int ctc_exponent(float x) { return int((__float_as_uint(x) >> 23) & 0xffu) - 127; }
+constexpr float kCtcNeg = -1.0e30f;                  // log2 of "no mass"; finite, so that differences are never NaN
+// log2(2^x + 2^y)
+ISP_DEVINL float ctc_lse2(float x, float y) { return fmaxf(x, y) + ctc_lg2(1.0f + ctc_ex2(-fabsf(x - y))); }
 
 // Per-lane ring of prefetched rows in shared memory: a lane copies the words of its own frames with 4 B async copies and
 // reads only what it copied itself, so cp.async.wait_group is all the synchronisation there is.  Depth 8: a step takes a
@@ -90,11 +91,11 @@ ctc_rownorm_kernel(const float* __restrict__ logits, const int64_t* __restrict__
 }
 
 // ---- forward variables ----------------------------------------------------------------------------------------------
-// Workspace layout: alpha (B, T1max + 31, 32, G) float (labels, by forward step), exps likewise int, z2 (B, T1max) float.
+// Workspace layout: alpha (B, T1max + 31, 32, G) float (log2 of the labels' forward variables, by forward step), z2 (B, T1max).
 template <int G>
 __global__ void __launch_bounds__(128)
 ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
-                 const int64_t* __restrict__ mel_len, float* __restrict__ alpha_ws, int* __restrict__ exp_ws,
+                 const int64_t* __restrict__ mel_len, float* __restrict__ alpha_ws,
                  float* __restrict__ nll, int B, int T1max, int T2max, float blank2) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -106,16 +107,13 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
     const float* xb = logits + (size_t)b * T1max * T2max;
     const float* zb = z2 + (size_t)b * T1max;
     float* ab = alpha_ws ? alpha_ws + (size_t)b * (T1max + 31) * (32 * G) : nullptr;      // [step][lane][G]
-    int* eb = exp_ws ? exp_ws + (size_t)b * (T1max + 31) * (32 * G) : nullptr;
 
-    float A[G], Bk[G];                 // label_j, blank_j of the previous frame, times 2^-E[j]
-    int E[G];
+    float A[G], Bk[G];                 // log2 of label_j, blank_j of the previous frame
 #pragma unroll
-    for (int g = 0; g < G; ++g) { A[g] = 0.0f; Bk[g] = 0.0f; E[g] = 0; }
-    if (lane == 0) Bk[0] = 1.0f;       // virtual frame -1: all the mass in the blank before token 0
-    // what the right neighbour takes: this lane's last label two steps ago, and its exponent
-    float h1v = 0.0f, h2v = 0.0f;
-    int h1e = 0, h2e = 0;
+    for (int g = 0; g < G; ++g) { A[g] = kCtcNeg; Bk[g] = kCtcNeg; }
+    if (lane == 0) Bk[0] = 0.0f;       // virtual frame -1: all the mass in the blank before token 0
+    // what the right neighbour takes: this lane's last label two steps ago
+    float h1v = kCtcNeg, h2v = kCtcNeg;
     // the rows of the lane's next frames, kCtcDepth - 1 steps ahead (addresses clamped; masks applied when the row is used)
     extern __shared__ float ctc_smem[];
     constexpr int W = G + 4;                                        // words per lane and stage: G logits, z (16 B slots)
@@ -140,76 +138,45 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
     for (int t = 0; t < steps; ++t) {
         const int i = t - lane;                                   // this lane's frame
         const float lv = __shfl_up_sync(0xffffffffu, h2v, 1);
-        const int le = __shfl_up_sync(0xffffffffu, h2e, 1);
         issue(t + kCtcDepth - 1);
         cp_async_wait_pending(kCtcDepth - 1);                     // the copies of step t have landed
         const float* row = ring + (t & (kCtcDepth - 1)) * 32 * W;
         const float zr = row[G];
-        float p[G];
+        float lp[G];                                              // log2 p_ij; "no mass" for tokens >= m
 #pragma unroll
-        for (int g = 0; g < G; ++g) p[g] = j0 + g < m ? ctc_ex2(fmaf(row[g], kCtcLog2e, -zr)) : 0.0f;
-        const float pB = ctc_ex2(blank2 - zr);
+        for (int g = 0; g < G; ++g) lp[g] = j0 + g < m ? fmaf(row[g], kCtcLog2e, -zr) : kCtcNeg;
+        const float lpB = blank2 - zr;
         if (i >= 0 && i < n) {
 #pragma unroll
             for (int g = G - 1; g >= 0; --g) {
-                // the left neighbour's label of the previous frame, brought to this token's scale
-                float am1 = g > 0 ? A[g - 1] : (lane == 0 ? 0.0f : lv);
-                const int em1 = g > 0 ? E[g - 1] : le;
-                float a = A[g], bk = Bk[g];
-                int e = E[g];
-                const bool inc = am1 > 0.0f;
-                e = (inc && a + bk == 0.0f) ? em1 : e;            // first mass to reach this token: adopt its scale
-                const int d = min(em1 - e, 41);
-                const bool big = inc && d > 40;                   // the neighbour is far above: move to its scale
-                const float f_own = big ? ctc_pow2(e - em1) : 1.0f;
-                const float f_in = big ? 1.0f : ctc_pow2(d);
-                e = big ? em1 : e;
-                const float s = fmaf(bk, f_own, am1 * f_in);
-                bk = pB * s;
-                a = p[g] * fmaf(a, f_own, s);
-                // renormalise the pair (a zero pair gets a meaningless exponent; it is adopted away above)
-                const int ex = ctc_exponent(fmaxf(a, bk));
-                const float sc = __int_as_float((127 - ex) << 23);                  // 2^-ex
-                a *= sc;
-                bk *= sc;
-                e += ex;
-                A[g] = a; Bk[g] = bk; E[g] = e;
+                const float am1 = g > 0 ? A[g - 1] : (lane == 0 ? kCtcNeg : lv);     // the left neighbour's label, previous frame
+                const float s = ctc_lse2(Bk[g], am1);
+                A[g] = fmaxf(lp[g] + ctc_lse2(A[g], s), kCtcNeg);
+                Bk[g] = fmaxf(lpB + s, kCtcNeg);
             }
             if (ab) {
-                // the gradient needs the labels' forward variables only; skewed order, 16 B vectors
+                // the gradient needs the labels' forward variables only; forward-step order, 16 B vectors
                 float4* dst = reinterpret_cast<float4*>(ab + (size_t)t * (32 * G) + j0);
-                int4* edst = reinterpret_cast<int4*>(eb + (size_t)t * (32 * G) + j0);
 #pragma unroll
-                for (int g = 0; g < G; g += 4) {
-                    dst[g >> 2] = make_float4(A[g], A[g + 1], A[g + 2], A[g + 3]);
-                    edst[g >> 2] = make_int4(E[g], E[g + 1], E[g + 2], E[g + 3]);
-                }
+                for (int g = 0; g < G; g += 4) dst[g >> 2] = make_float4(A[g], A[g + 1], A[g + 2], A[g + 3]);
             }
         }
-        h2v = h1v; h2e = h1e;
-        h1v = A[G - 1]; h1e = E[G - 1];
+        h2v = h1v;
+        h1v = A[G - 1];
     }
     // likelihood = label_{m-1} + blank_m after frame n-1 (every lane now holds its frame n-1)
     const int la = (m - 1) / G, lb = m / G;
-    float va = 0.0f, vb = 0.0f;
-    int ea = 0, ebk = 0;
+    float va = kCtcNeg, vb = kCtcNeg;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-        if (lane == la && g == (m - 1) - la * G) { va = A[g]; ea = E[g]; }
-        if (lane == lb && g == m - lb * G) { vb = Bk[g]; ebk = E[g]; }
+        if (lane == la && g == (m - 1) - la * G) va = A[g];
+        if (lane == lb && g == m - lb * G) vb = Bk[g];
     }
-    ea = __shfl_sync(0xffffffffu, ea, la);
-    ebk = __shfl_sync(0xffffffffu, ebk, lb);
     va = __shfl_sync(0xffffffffu, va, la);
     vb = __shfl_sync(0xffffffffu, vb, lb);
     if (lane == 0) {
-        float r = CUDART_INF_F;
-        if (va > 0.0f || vb > 0.0f) {
-            const int em = (va > 0.0f && vb > 0.0f) ? max(ea, ebk) : (va > 0.0f ? ea : ebk);
-            const float s = (va > 0.0f ? ctc_scale(va, ea - em) : 0.0f) + (vb > 0.0f ? ctc_scale(vb, ebk - em) : 0.0f);
-            r = -(log2f(s) + float(em)) * kCtcLn2;
-        }
-        nll[b] = r;                                                 // +inf: no alignment exists (mel_len < text_len)
+        const float l2 = ctc_lse2(va, vb);
+        nll[b] = l2 > 0.5f * kCtcNeg ? -l2 * kCtcLn2 : CUDART_INF_F;       // +inf: no alignment exists (mel_len < text_len)
     }
 }
 
@@ -223,7 +190,7 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
 template <int G>
 __global__ void __launch_bounds__(128)
 ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
-                     const int64_t* __restrict__ mel_len, const float* __restrict__ alpha_ws, const int* __restrict__ exp_ws,
+                     const int64_t* __restrict__ mel_len, const float* __restrict__ alpha_ws,
                      const float* __restrict__ nll, const float* __restrict__ grad_scale, float* __restrict__ grad,
                      int B, int T1max, int T2max, float blank2) {
     const int lane = threadIdx.x & 31;
@@ -236,7 +203,6 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
     const float* xb = logits + (size_t)b * T1max * T2max;
     const float* zb = z2 + (size_t)b * T1max;
     const float* ab = alpha_ws + (size_t)b * (T1max + 31) * (32 * G);                     // [forward step][lane][G]
-    const int* eb = exp_ws + (size_t)b * (T1max + 31) * (32 * G);
     float* gb = grad + (size_t)b * T1max * T2max;
     const float nl = nll[b];
     const float gs = grad_scale[b];
@@ -251,17 +217,15 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
     }
     const float log2P = -nl * kCtcLog2e;
 
-    float Ha[G], Hb[G];                // H_{i+1}(label_j), H_{i+1}(blank_j), times 2^-F[j]
-    int F[G];
+    float Ha[G], Hb[G];                // log2 of H_{i+1}(label_j), H_{i+1}(blank_j)
 #pragma unroll
-    for (int g = 0; g < G; ++g) { Ha[g] = 0.0f; Hb[g] = 0.0f; F[g] = 0; }
+    for (int g = 0; g < G; ++g) { Ha[g] = kCtcNeg; Hb[g] = kCtcNeg; }
     const int lb = m / G;
 #pragma unroll
-    for (int g = 0; g < G; ++g) if (lane == lb && g == m - lb * G) Hb[g] = 1.0f;      // virtual frame n: blank_m
-    float h1a = 0.0f, h1b = 0.0f, h2a = 0.0f, h2b = 0.0f;          // this lane's first token, one and two steps ago
-    int h1e = 0, h2e = 0;
+    for (int g = 0; g < G; ++g) if (lane == lb && g == m - lb * G) Hb[g] = 0.0f;      // virtual frame n: blank_m
+    float h1a = Ha[0], h1b = Hb[0], h2a = Ha[0], h2b = Hb[0];      // this lane's first token, one and two steps ago
     extern __shared__ float ctc_smem[];
-    constexpr int W = 3 * G + 4;                                    // logits, alpha labels, alpha exponents, z (16 B slots)
+    constexpr int W = 2 * G + 4;                                    // logits, alpha labels, z (16 B slots)
     float* ring = ctc_smem + (size_t)(threadIdx.x >> 5) * kCtcDepth * 32 * W + lane * W;
     const bool vec = (T2max & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
     auto issue = [&](int step) {
@@ -270,7 +234,6 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
         float* dst = ring + (step & (kCtcDepth - 1)) * 32 * W;
         const float* src = xb + (size_t)i * T2max;
         const float* asrc = ab + (size_t)ta * (32 * G) + j0;
-        const int* esrc = eb + (size_t)ta * (32 * G) + j0;
         if (vec) {
 #pragma unroll
             for (int g = 0; g < G; g += 4) ctc_cp16(dst + g, src + min(j0 + g, T2max - 4));
@@ -279,70 +242,40 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
             for (int g = 0; g < G; ++g) ctc_cp4(dst + g, src + min(j0 + g, T2max - 1));
         }
 #pragma unroll
-        for (int g = 0; g < G; g += 4) {
-            ctc_cp16(dst + G + g, asrc + g);
-            ctc_cp16(dst + 2 * G + g, esrc + g);
-        }
-        ctc_cp4(dst + 3 * G, zb + i);
+        for (int g = 0; g < G; g += 4) ctc_cp16(dst + G + g, asrc + g);
+        ctc_cp4(dst + 2 * G, zb + i);
         cp_async_commit();
     };
     for (int st = 0; st < kCtcDepth - 1; ++st) issue(st);
-    h1a = Ha[0]; h1b = Hb[0];
-    h2a = h1a; h2b = h1b;
     const int steps = n + 31;
     for (int t = 0; t < steps; ++t) {
         const int i = n - 1 - t + 31 - lane;
         const float rav = __shfl_down_sync(0xffffffffu, h2a, 1);
         const float rbv = __shfl_down_sync(0xffffffffu, h2b, 1);
-        const int re = __shfl_down_sync(0xffffffffu, h2e, 1);
         issue(t + kCtcDepth - 1);
         cp_async_wait_pending(kCtcDepth - 1);                     // the copies of step t have landed
         const float* row = ring + (t & (kCtcDepth - 1)) * 32 * W;
-        const float zr = row[3 * G];
-        float psm[G], a_cur[G];
-        int e_cur[G];
+        const float zr = row[2 * G];
+        float lp[G], a_cur[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            psm[g] = j0 + g < T2max ? ctc_ex2(fmaf(row[g], kCtcLog2e, -zr)) : 0.0f;   // softmax over all T2max columns
+            lp[g] = j0 + g < T2max ? fmaf(row[g], kCtcLog2e, -zr) : kCtcNeg;       // log2 softmax over all T2max columns
             a_cur[g] = row[G + g];
-            e_cur[g] = __float_as_int(row[2 * G + g]);
         }
-        const float pB = ctc_ex2(blank2 - zr);
+        const float lpB = blank2 - zr;
         if (i >= 0 && i < n) {
             float gr[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                // the right neighbour's pair of frame i + 1, brought to this token's scale
-                float na = g + 1 < G ? Ha[g + 1] : (lane == 31 ? 0.0f : rav);
-                float nb = g + 1 < G ? Hb[g + 1] : (lane == 31 ? 0.0f : rbv);
-                const int en = g + 1 < G ? F[g + 1] : re;
-                float ha = Ha[g], hb = Hb[g];
-                int f = F[g];
-                const bool inc = na > 0.0f || nb > 0.0f;
-                f = (inc && ha + hb == 0.0f) ? en : f;
-                const int d = min(en - f, 41);
-                const bool big = inc && d > 40;
-                const float f_own = big ? ctc_pow2(f - en) : 1.0f;
-                const float f_in = big ? 1.0f : ctc_pow2(d);
-                f = big ? en : f;
-                ha *= f_own;
-                hb *= f_own;
-                na *= f_in;
-                nb *= f_in;
-                const float bt_a = ha + nb + na;
-                const float bt_b = hb + ha;
-                // posterior of label_j at frame i: alpha carries 2^e_cur, beta 2^f.  (The exponent is clamped: a token the
-                // forward pass never reached holds zeros under a stale exponent, and 0 * inf is not 0.)
-                const float post = a_cur[g] * bt_a * ctc_ex2(fminf(float(e_cur[g] + f) - log2P, 126.0f));
-                gr[g] = gs * (psm[g] - post);
-                ha = (j0 + g < m ? psm[g] : 0.0f) * bt_a;
-                hb = pB * bt_b;
-                const int ex = ctc_exponent(fmaxf(ha, hb));
-                const float sc = __int_as_float((127 - ex) << 23);
-                ha *= sc;
-                hb *= sc;
-                f += ex;
-                Ha[g] = ha; Hb[g] = hb; F[g] = f;
+                const float na = g + 1 < G ? Ha[g + 1] : (lane == 31 ? kCtcNeg : rav);      // the right neighbour's pair, frame i + 1
+                const float nb = g + 1 < G ? Hb[g + 1] : (lane == 31 ? kCtcNeg : rbv);
+                const float bt_a = ctc_lse2(Ha[g], ctc_lse2(nb, na));
+                const float bt_b = ctc_lse2(Hb[g], Ha[g]);
+                // posterior of label_j at frame i = alpha * beta / P (a probability: the exponent is <= 0 up to rounding)
+                const float post = ctc_ex2(fminf(a_cur[g] + bt_a - log2P, 1.0f));
+                gr[g] = gs * (ctc_ex2(lp[g]) - post);
+                Ha[g] = fmaxf((j0 + g < m ? lp[g] : kCtcNeg) + bt_a, kCtcNeg);
+                Hb[g] = fmaxf(lpB + bt_b, kCtcNeg);
             }
             float* grow = gb + (size_t)i * T2max + j0;
             if (vec && (reinterpret_cast<uintptr_t>(grad) & 15) == 0) {
@@ -354,8 +287,8 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
                 for (int g = 0; g < G; ++g) if (j0 + g < T2max) grow[g] = gr[g];
             }
         }
-        h2a = h1a; h2b = h1b; h2e = h1e;
-        h1a = Ha[0]; h1b = Hb[0]; h1e = F[0];
+        h2a = h1a; h2b = h1b;
+        h1a = Ha[0]; h1b = Hb[0];
     }
 }
 
@@ -366,22 +299,21 @@ static int ctc_group_padded(int T2max) {
     return g <= 4 ? 4 : (g <= 8 ? 8 : (g <= 12 ? 12 : (g <= 16 ? 16 : 0)));
 }
 
-static int ctc_warps_per_cta(int G) { return G <= 8 ? 4 : 2; }     // the backward ring is 1 KB * (3G + 4) per warp
+static int ctc_warps_per_cta(int G) { return G <= 8 ? 4 : 2; }     // the backward ring is 1 KB * (2G + 4) per warp
 
 size_t ctc_workspace_bytes(int B, int T1max, int T2max) {
     const int G = ctc_group_padded(T2max);
     if (B <= 0 || T1max <= 0 || T2max <= 0 || G == 0) return 0;
     const size_t rows = size_t(B) * T1max, srows = size_t(B) * (T1max + 31);
-    return srows * 32 * G * sizeof(float) + srows * 32 * G * sizeof(int) + rows * sizeof(float) + 256;
+    return srows * 32 * G * sizeof(float) + rows * sizeof(float) + 256;
 }
 
-struct CtcWs { float* alpha; int* exps; float* z2; };
+struct CtcWs { float* alpha; float* z2; };
 static CtcWs ctc_carve(void* ws, int B, int T1max, int G) {
     const size_t srows = size_t(B) * (T1max + 31);
     CtcWs w;
     w.alpha = static_cast<float*>(ws);
-    w.exps = reinterpret_cast<int*>(w.alpha + srows * 32 * G);
-    w.z2 = reinterpret_cast<float*>(w.exps + srows * 32 * G);
+    w.z2 = w.alpha + srows * 32 * G;
     return w;
 }
 
@@ -412,7 +344,7 @@ int ctc_forward(const float* logits, const int64_t* text_len, const int64_t* mel
         const size_t sm = size_t(wpc) * kCtcDepth * 32 * (GG + 4) * sizeof(float);                                         \
         cudaError_t ea = cudaFuncSetAttribute(ctc_alpha_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));    \
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(ctc_alpha_kernel)");                               \
-        ctc_alpha_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, B, T1max, T2max, blank2); \
+        ctc_alpha_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, nll, B, T1max, T2max, blank2); \
     }
     switch (G) {
         case 4: ISP_CTC_ALPHA(4) break;
@@ -439,10 +371,10 @@ int ctc_backward(const float* logits, const int64_t* text_len, const int64_t* me
     const int grid = (B + wpc - 1) / wpc;
 #define ISP_CTC_BETA(GG)                                                                                                    \
     {                                                                                                                        \
-        const size_t sm = size_t(wpc) * kCtcDepth * 32 * (3 * GG + 4) * sizeof(float);                                     \
+        const size_t sm = size_t(wpc) * kCtcDepth * 32 * (2 * GG + 4) * sizeof(float);                                     \
         cudaError_t ea = cudaFuncSetAttribute(ctc_beta_grad_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)); \
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(ctc_beta_grad_kernel)");                            \
-        ctc_beta_grad_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.exps, nll, grad_scale, \
+        ctc_beta_grad_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, nll, grad_scale, \
                                                                  grad_logits, B, T1max, T2max, blank2);                       \
     }
     switch (G) {

@@ -1,8 +1,9 @@
 """Forward-sum (CTC) alignment loss: the CUDA path (isp_ctc_forward / isp_ctc_backward through the C ABI) against the oracle
 (oracle/ctc.py: the reference's op sequence, tts/models/acoustic/loss.py:41-79, with torch on the CPU in float64).
 
-Tolerances (fp32 kernels, linear-domain sums in block floating point): nll within 2e-5 relative + 1e-4 absolute;
-gradient within 2e-4 of the largest gradient entry of the utterance.
+Tolerances (fp32 kernels, log2-domain recursion with ex2.approx / lg2.approx): nll within 2e-5 relative + 1e-4 absolute;
+gradient within 5e-4 of the largest gradient entry of the utterance (a posterior is 2^(alpha + beta - log2 P) with the
+three terms around 1e3 in the hardest case here -- mel_len == text_len == 200 -- where one fp32 ulp is already 1.2e-4).
 """
 import numpy as np
 import pytest
@@ -51,7 +52,7 @@ def test_ctc_matches_oracle(cuda_device, shape):
     assert torch.allclose(nll, ref, rtol=2e-5, atol=1e-4), (nll, ref)
     for b in range(B):
         scale = gref[b].abs().max().item()
-        assert (g[b] - gref[b]).abs().max().item() <= 2e-4 * scale, (b, (g[b] - gref[b]).abs().max().item(), scale)
+        assert (g[b] - gref[b]).abs().max().item() <= 5e-4 * scale, (b, (g[b] - gref[b]).abs().max().item(), scale)
     assert g[0, ml[0]:].abs().sum().item() == 0.0                         # frames past the utterance carry no gradient
 
 
@@ -68,7 +69,7 @@ def test_ctc_noise_and_degenerate(cuda_device):
     assert torch.allclose(nll[ok], ref[ok], rtol=2e-5, atol=1e-4), (nll, ref)
     assert g[3].abs().sum().item() == 0.0
     for b in ok:
-        assert (g[b] - gref[b]).abs().max().item() <= 2e-4 * gref[b].abs().max().item()
+        assert (g[b] - gref[b]).abs().max().item() <= 5e-4 * gref[b].abs().max().item()
 
 
 def test_ctc_module_matches_reference_reduction(cuda_device):
