@@ -62,6 +62,9 @@ constexpr int kCtcDepth = 8;
 ISP_DEVINL void ctc_cp4(float* sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
 }
+ISP_DEVINL void ctc_cp8(float* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
 ISP_DEVINL void ctc_cp16(float* sdst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
 }
@@ -86,16 +89,20 @@ ctc_rownorm_kernel(const float* __restrict__ logits, const int64_t* __restrict__
         for (int j = lane; j < T2max; j += 32) s += ctc_ex2(fmaf(__ldg(x + j), kCtcLog2e, -m));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) z2[row] = m + log2f(s);
+        // {Z_i, M_i}: the recursions use log2 p relative to the row's LARGEST term (M_i), so that the forward and backward
+        // variables stay within tens of units instead of drifting by log2 p per frame (fp32 resolution); the softmax
+        // probabilities of the gradient use Z_i, and the forward pass adds the sum of Z_i - M_i back into nll
+        if (lane == 0) reinterpret_cast<float2*>(z2)[row] = make_float2(m + log2f(s), m);
     }
 }
 
 // ---- forward variables ----------------------------------------------------------------------------------------------
-// Workspace layout: alpha (B, T1max + 31, 32, G) float (log2 of the labels' forward variables, by forward step), z2 (B, T1max).
+// Workspace layout: alpha (B, T1max + 31, 32, G) float (log2 of the labels' forward variables, by forward step), z2 (B, T1max)
+// float2 {Z_i, M_i}, l2p (B) float.
 template <int G>
 __global__ void __launch_bounds__(128)
 ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
-                 const int64_t* __restrict__ mel_len, float* __restrict__ alpha_ws,
+                 const int64_t* __restrict__ mel_len, float* __restrict__ alpha_ws, float* __restrict__ l2p,
                  float* __restrict__ nll, int B, int T1max, int T2max, float blank2) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -105,7 +112,7 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
     const int m = int(m64 < 1 ? 1 : (m64 > T2max ? T2max : m64));      // tokens
     const int j0 = lane * G;
     const float* xb = logits + (size_t)b * T1max * T2max;
-    const float* zb = z2 + (size_t)b * T1max;
+    const float2* zb = reinterpret_cast<const float2*>(z2) + (size_t)b * T1max;
     float* ab = alpha_ws ? alpha_ws + (size_t)b * (T1max + 31) * (32 * G) : nullptr;      // [step][lane][G]
 
     float A[G], Bk[G];                 // log2 of label_j, blank_j of the previous frame
@@ -130,10 +137,11 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
 #pragma unroll
             for (int g = 0; g < G; ++g) ctc_cp4(dst + g, src + min(j0 + g, T2max - 1));
         }
-        ctc_cp4(dst + G, zb + i);
+        ctc_cp8(dst + G, zb + i);
         cp_async_commit();
     };
     for (int st = 0; st < kCtcDepth - 1; ++st) issue(st);
+    float osum = 0.0f;                                            // sum of Z_i - M_i over the frames (lane 0 sees them all)
     const int steps = n + 31;
     for (int t = 0; t < steps; ++t) {
         const int i = t - lane;                                   // this lane's frame
@@ -141,12 +149,13 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
         issue(t + kCtcDepth - 1);
         cp_async_wait_pending(kCtcDepth - 1);                     // the copies of step t have landed
         const float* row = ring + (t & (kCtcDepth - 1)) * 32 * W;
-        const float zr = row[G];
-        float lp[G];                                              // log2 p_ij; "no mass" for tokens >= m
+        const float zr = row[G], mr = row[G + 1];
+        float lp[G];                                              // log2 p_ij + (Z_i - M_i); "no mass" for tokens >= m
 #pragma unroll
-        for (int g = 0; g < G; ++g) lp[g] = j0 + g < m ? fmaf(row[g], kCtcLog2e, -zr) : kCtcNeg;
-        const float lpB = blank2 - zr;
+        for (int g = 0; g < G; ++g) lp[g] = j0 + g < m ? fmaf(row[g], kCtcLog2e, -mr) : kCtcNeg;
+        const float lpB = blank2 - mr;
         if (i >= 0 && i < n) {
+            osum += zr - mr;
 #pragma unroll
             for (int g = G - 1; g >= 0; --g) {
                 const float am1 = g > 0 ? A[g - 1] : (lane == 0 ? kCtcNeg : lv);     // the left neighbour's label, previous frame
@@ -175,8 +184,9 @@ ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ z2,
     va = __shfl_sync(0xffffffffu, va, la);
     vb = __shfl_sync(0xffffffffu, vb, lb);
     if (lane == 0) {
-        const float l2 = ctc_lse2(va, vb);
-        nll[b] = l2 > 0.5f * kCtcNeg ? -l2 * kCtcLn2 : CUDART_INF_F;       // +inf: no alignment exists (mel_len < text_len)
+        const float l2 = ctc_lse2(va, vb);                                  // log2 of P * 2^osum
+        nll[b] = l2 > 0.5f * kCtcNeg ? (osum - l2) * kCtcLn2 : CUDART_INF_F;     // +inf: no alignment exists (mel_len < text_len)
+        if (l2p) l2p[b] = l2;
     }
 }
 
@@ -191,7 +201,8 @@ template <int G>
 __global__ void __launch_bounds__(128)
 ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__ z2, const int64_t* __restrict__ text_len,
                      const int64_t* __restrict__ mel_len, const float* __restrict__ alpha_ws,
-                     const float* __restrict__ nll, const float* __restrict__ grad_scale, float* __restrict__ grad,
+                     const float* __restrict__ l2p, const float* __restrict__ nll, const float* __restrict__ grad_scale,
+                     float* __restrict__ grad,
                      int B, int T1max, int T2max, float blank2) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -201,7 +212,7 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
     const int m = int(m64 < 1 ? 1 : (m64 > T2max ? T2max : m64));
     const int j0 = lane * G;
     const float* xb = logits + (size_t)b * T1max * T2max;
-    const float* zb = z2 + (size_t)b * T1max;
+    const float2* zb = reinterpret_cast<const float2*>(z2) + (size_t)b * T1max;
     const float* ab = alpha_ws + (size_t)b * (T1max + 31) * (32 * G);                     // [forward step][lane][G]
     float* gb = grad + (size_t)b * T1max * T2max;
     const float nl = nll[b];
@@ -215,7 +226,7 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
         for (size_t k = lane; k < cnt; k += 32) z[k] = 0.0f;
         if (dead) return;
     }
-    const float log2P = -nl * kCtcLog2e;
+    const float log2P = l2p[b];                                     // log2 of P * 2^(sum of Z_i - M_i): the scale the variables carry
 
     float Ha[G], Hb[G];                // log2 of H_{i+1}(label_j), H_{i+1}(blank_j)
 #pragma unroll
@@ -243,7 +254,7 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
         }
 #pragma unroll
         for (int g = 0; g < G; g += 4) ctc_cp16(dst + G + g, asrc + g);
-        ctc_cp4(dst + 2 * G, zb + i);
+        ctc_cp8(dst + 2 * G, zb + i);
         cp_async_commit();
     };
     for (int st = 0; st < kCtcDepth - 1; ++st) issue(st);
@@ -255,14 +266,15 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
         issue(t + kCtcDepth - 1);
         cp_async_wait_pending(kCtcDepth - 1);                     // the copies of step t have landed
         const float* row = ring + (t & (kCtcDepth - 1)) * 32 * W;
-        const float zr = row[2 * G];
+        const float zr = row[2 * G], mr = row[2 * G + 1];
         float lp[G], a_cur[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            lp[g] = j0 + g < T2max ? fmaf(row[g], kCtcLog2e, -zr) : kCtcNeg;       // log2 softmax over all T2max columns
+            lp[g] = j0 + g < T2max ? fmaf(row[g], kCtcLog2e, -mr) : kCtcNeg;       // relative to the row's largest term
             a_cur[g] = row[G + g];
         }
-        const float lpB = blank2 - zr;
+        const float lpB = blank2 - mr;
+        const float dz = mr - zr;                                                   // log2 softmax = lp + dz
         if (i >= 0 && i < n) {
             float gr[G];
 #pragma unroll
@@ -273,7 +285,7 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
                 const float bt_b = ctc_lse2(Hb[g], Ha[g]);
                 // posterior of label_j at frame i = alpha * beta / P (a probability: the exponent is <= 0 up to rounding)
                 const float post = ctc_ex2(fminf(a_cur[g] + bt_a - log2P, 1.0f));
-                gr[g] = gs * (ctc_ex2(lp[g]) - post);
+                gr[g] = gs * (ctc_ex2(lp[g] + dz) - post);
                 Ha[g] = fmaxf((j0 + g < m ? lp[g] : kCtcNeg) + bt_a, kCtcNeg);
                 Hb[g] = fmaxf(lpB + bt_b, kCtcNeg);
             }
@@ -305,15 +317,16 @@ size_t ctc_workspace_bytes(int B, int T1max, int T2max) {
     const int G = ctc_group_padded(T2max);
     if (B <= 0 || T1max <= 0 || T2max <= 0 || G == 0) return 0;
     const size_t rows = size_t(B) * T1max, srows = size_t(B) * (T1max + 31);
-    return srows * 32 * G * sizeof(float) + rows * sizeof(float) + 256;
+    return srows * 32 * G * sizeof(float) + rows * sizeof(float2) + size_t(B) * sizeof(float) + 256;
 }
 
-struct CtcWs { float* alpha; float* z2; };
+struct CtcWs { float* alpha; float* z2; float* l2p; };
 static CtcWs ctc_carve(void* ws, int B, int T1max, int G) {
     const size_t srows = size_t(B) * (T1max + 31);
     CtcWs w;
     w.alpha = static_cast<float*>(ws);
-    w.z2 = w.alpha + srows * 32 * G;
+    w.z2 = w.alpha + srows * 32 * G;                       // (B, T1max) float2 {Z_i, M_i}
+    w.l2p = w.z2 + size_t(B) * T1max * 2;
     return w;
 }
 
@@ -344,7 +357,7 @@ int ctc_forward(const float* logits, const int64_t* text_len, const int64_t* mel
         const size_t sm = size_t(wpc) * kCtcDepth * 32 * (GG + 4) * sizeof(float);                                         \
         cudaError_t ea = cudaFuncSetAttribute(ctc_alpha_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm));    \
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(ctc_alpha_kernel)");                               \
-        ctc_alpha_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, nll, B, T1max, T2max, blank2); \
+        ctc_alpha_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.l2p, nll, B, T1max, T2max, blank2); \
     }
     switch (G) {
         case 4: ISP_CTC_ALPHA(4) break;
@@ -374,7 +387,7 @@ int ctc_backward(const float* logits, const int64_t* text_len, const int64_t* me
         const size_t sm = size_t(wpc) * kCtcDepth * 32 * (2 * GG + 4) * sizeof(float);                                     \
         cudaError_t ea = cudaFuncSetAttribute(ctc_beta_grad_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm)); \
         if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute(ctc_beta_grad_kernel)");                            \
-        ctc_beta_grad_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, nll, grad_scale, \
+        ctc_beta_grad_kernel<GG><<<grid, 32 * wpc, sm, stream>>>(logits, w.z2, text_len, mel_len, w.alpha, w.l2p, nll, grad_scale, \
                                                                  grad_logits, B, T1max, T2max, blank2);                       \
     }
     switch (G) {

@@ -1,9 +1,9 @@
 """Forward-sum (CTC) alignment loss: the CUDA path (isp_ctc_forward / isp_ctc_backward through the C ABI) against the oracle
 (oracle/ctc.py: the reference's op sequence, tts/models/acoustic/loss.py:41-79, with torch on the CPU in float64).
 
-Tolerances (fp32 kernels, log2-domain recursion with ex2.approx / lg2.approx): nll within 2e-5 relative + 1e-4 absolute;
-gradient within 5e-4 of the largest gradient entry of the utterance (a posterior is 2^(alpha + beta - log2 P) with the
-three terms around 1e3 in the hardest case here -- mel_len == text_len == 200 -- where one fp32 ulp is already 1.2e-4).
+Tolerances (fp32 kernels, log2-domain recursion with ex2.approx / lg2.approx, variables kept relative to each frame's
+largest term): nll within 2e-5 relative + 1e-4 absolute; gradient within 5e-4 of the largest gradient entry of the
+utterance (measured: 1e-4 .. 2e-4 on the hardest shapes here; torch's own fp32 CTC differs from float64 by as much).
 """
 import numpy as np
 import pytest
@@ -42,7 +42,8 @@ def run_both(x, tl, ml, dev, blank=-1.0):
     return nll.detach().cpu().double(), xt.grad.cpu().double(), ref.detach(), xo.grad
 
 
-@pytest.mark.parametrize("shape", [(3, 40, 9), (4, 150, 40), (2, 300, 70), (2, 64, 130), (1, 200, 200)])
+@pytest.mark.parametrize("shape", [(3, 40, 9), (4, 150, 40), (2, 300, 70), (2, 64, 130), (1, 200, 200),
+                                   (2, 90, 37), (3, 77, 3), (2, 700, 300), (1, 1200, 500)])
 def test_ctc_matches_oracle(cuda_device, shape):
     B, T1, T2 = shape
     tl, ml = synth.lengths(B, T2, T1, True, 91 + T2)
@@ -80,3 +81,15 @@ def test_ctc_module_matches_reference_reduction(cuda_device):
     loss = AttentionCTCLoss()(torch.from_numpy(x).to(cuda_device), torch.from_numpy(tl).to(cuda_device), torch.from_numpy(ml).to(cuda_device))
     ref = octc.attention_ctc_loss(torch.from_numpy(x), torch.from_numpy(tl), torch.from_numpy(ml))
     assert abs(loss.item() - ref.item()) <= 2e-5 * abs(ref.item()) + 1e-5
+
+
+def test_ctc_full_size_cfg3_shapes(cuda_device):
+    """BASELINE cfg3 shapes (<= 200 tokens x <= 1000 frames, ragged, one utterance at the maximum), a batch the float64
+    oracle finishes in seconds."""
+    B, T1, T2 = 8, 1000, 200
+    tl, ml = synth.lengths(B, T2, T1, True, 1237)
+    x = realistic_logits(B, T1, T2, tl, ml, 1238)
+    nll, g, ref, gref = run_both(x, tl, ml, cuda_device)
+    assert torch.allclose(nll, ref, rtol=2e-5, atol=1e-4), (nll, ref)
+    for b in range(B):
+        assert (g[b] - gref[b]).abs().max().item() <= 5e-4 * gref[b].abs().max().item()
