@@ -421,6 +421,7 @@ def run_ours(args, w):
         # f-4: forward-sum (CTC) loss and its gradient vs the reference's op sequence on the GPU (loss.py:59-79:
         # F.pad + log_softmax + transpose + nn.CTCLoss(zero_infinity=True)), same logits
         from isp_tts_b200.ctc import attention_ctc_loss
+        from isp_tts_b200._lib import IspError
         t_ours, t_ref = [], []
         tgt = torch.arange(1, T2 + 1, device=dev)[None].expand(B, -1).clone()
         tgt[tgt > tl_dev[:, None]] = 0
@@ -428,7 +429,11 @@ def run_ours(args, w):
             xa = logits_b.detach().clone().requires_grad_(True)
             xb2 = logits_b.detach().clone().requires_grad_(True)
             ev[0].record()
-            la = attention_ctc_loss(xa, tl_dev, ml_dev)
+            try:
+                la = attention_ctc_loss(xa, tl_dev, ml_dev)
+            except IspError as exc:                      # a shape the next-row kernel does not cover: say so, measure the rest
+                bwd["f-4 forward-sum (CTC) loss"] = {"unsupported": str(exc)}
+                break
             la.backward()
             ev[1].record()
             lp = torch.nn.functional.log_softmax(torch.nn.functional.pad(xb2, (1, 0), value=-1.0), dim=2).transpose(0, 1)
@@ -438,12 +443,14 @@ def run_ours(args, w):
             torch.cuda.synchronize()
             if it >= 2:
                 t_ours.append(ev[0].elapsed_time(ev[1])); t_ref.append(ev[1].elapsed_time(ev[2]))
-        if abs(la.item() - lb2.item()) > 1e-4 * max(1.0, abs(lb2.item())):
-            raise RuntimeError("forward-sum loss differs from torch CTC: %r vs %r" % (la.item(), lb2.item()))
-        gerr = float((xa.grad - xb2.grad).abs().max() / xb2.grad.abs().max())
-        bwd["f-4 forward-sum (CTC) loss"] = {"isp_ctc_forward_backward_ms": float(np.mean(t_ours)), "torch_reference_sequence_ms": float(np.mean(t_ref)),
-                                             "value": la.item(), "grad_max_rel_diff_vs_torch_fp32": gerr}
-        del logits_b, xa, xb2, lp
+        if "f-4 forward-sum (CTC) loss" not in bwd:
+            if abs(la.item() - lb2.item()) > 1e-4 * max(1.0, abs(lb2.item())):
+                raise RuntimeError("forward-sum loss differs from torch CTC: %r vs %r" % (la.item(), lb2.item()))
+            gerr = float((xa.grad - xb2.grad).abs().max() / xb2.grad.abs().max())
+            bwd["f-4 forward-sum (CTC) loss"] = {"isp_ctc_forward_backward_ms": float(np.mean(t_ours)),
+                                                 "torch_reference_sequence_ms": float(np.mean(t_ref)),
+                                                 "value": la.item(), "grad_max_rel_diff_vs_torch_fp32": gerr}
+        del logits_b, xa, xb2
 
     if rank != 0:
         if world > 1:

@@ -116,7 +116,7 @@ int    isp_temporal_average(const float* x, const int64_t* durations, float* out
  * the same `ws` afterwards, writes grad_logits[b, i, j] = grad_scale[b] * d nll[b] / d attn_logits[b, i, j] for the whole
  * (B, T1max, T2max) tensor (zeros past mel_len[b]; all zeros for an utterance whose nll is +inf -- zero_infinity).  The
  * reference's loss is mean_b(nll[b] / text_len[b]), so grad_scale[b] = upstream / (B * text_len[b]).
- * attn_logits (B, T1max, T2max) fp32 contiguous; ws 16 B aligned, isp_ctc_workspace_bytes(...) bytes; T2max <= 511. */
+ * attn_logits (B, T1max, T2max) fp32 contiguous; ws 16 B aligned, isp_ctc_workspace_bytes(...) bytes; T2max <= 639. */
 size_t isp_ctc_workspace_bytes(int B, int T1max, int T2max);
 int    isp_ctc_forward(const float* attn_logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                        float blank_logprob, float* nll, void* ws, size_t ws_bytes, void* stream);

@@ -308,7 +308,7 @@ ctc_beta_grad_kernel(const float* __restrict__ logits, const float* __restrict__
 static int ctc_group(int T2max) { return (T2max + 1 + 31) / 32; }          // tokens per lane (the virtual token T2 included)
 static int ctc_group_padded(int T2max) {
     const int g = ctc_group(T2max);
-    return g <= 4 ? 4 : (g <= 8 ? 8 : (g <= 12 ? 12 : (g <= 16 ? 16 : 0)));
+    return g <= 4 ? 4 : (g <= 8 ? 8 : (g <= 12 ? 12 : (g <= 16 ? 16 : (g <= 20 ? 20 : 0))));
 }
 
 static int ctc_warps_per_cta(int G) { return G <= 8 ? 4 : 2; }     // the backward ring is 1 KB * (2G + 4) per warp
@@ -334,7 +334,7 @@ static int ctc_check(const char* who, const float* logits, const int64_t* text_l
                      const void* ws, size_t ws_bytes) {
     if (!logits || !text_len || !mel_len || !ws) { set_error("%s: null pointer", who); return ISP_ERR_INVALID; }
     if (B <= 0 || T1max <= 0 || T2max <= 0) { set_error("%s: sizes must be positive", who); return ISP_ERR_INVALID; }
-    if (ctc_group_padded(T2max) == 0) { set_error("%s: T2max=%d > 511 text tokens is not covered", who, T2max); return ISP_ERR_UNSUPPORTED; }
+    if (ctc_group_padded(T2max) == 0) { set_error("%s: T2max=%d > 639 text tokens is not covered", who, T2max); return ISP_ERR_UNSUPPORTED; }
     if (ws_bytes < ctc_workspace_bytes(B, T1max, T2max)) { set_error("%s: workspace of %zu B required, got %zu", who, ctc_workspace_bytes(B, T1max, T2max), ws_bytes); return ISP_ERR_WORKSPACE; }
     if (reinterpret_cast<uintptr_t>(ws) & 15) { set_error("%s: workspace must be 16 B aligned", who); return ISP_ERR_INVALID; }
     return 0;
@@ -363,7 +363,8 @@ int ctc_forward(const float* logits, const int64_t* text_len, const int64_t* mel
         case 4: ISP_CTC_ALPHA(4) break;
         case 8: ISP_CTC_ALPHA(8) break;
         case 12: ISP_CTC_ALPHA(12) break;
-        default: ISP_CTC_ALPHA(16) break;
+        case 16: ISP_CTC_ALPHA(16) break;
+        default: ISP_CTC_ALPHA(20) break;
     }
 #undef ISP_CTC_ALPHA
     cudaError_t e = cudaGetLastError();
@@ -394,7 +395,8 @@ int ctc_backward(const float* logits, const int64_t* text_len, const int64_t* me
         case 4: ISP_CTC_BETA(4) break;
         case 8: ISP_CTC_BETA(8) break;
         case 12: ISP_CTC_BETA(12) break;
-        default: ISP_CTC_BETA(16) break;
+        case 16: ISP_CTC_BETA(16) break;
+        default: ISP_CTC_BETA(20) break;
     }
 #undef ISP_CTC_BETA
     cudaError_t e = cudaGetLastError();
