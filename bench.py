@@ -349,6 +349,25 @@ def run_ours(args, w):
     if int(dur_host.sum()) != int(ml.sum()):
         raise RuntimeError("durations do not sum to the mel lengths")
 
+    # ---- the one collective of the path (outside every timed region): NCCL all-gather of the durations when the caller
+    # wants a single tensor; checked against the lengths every rank holds ---------------------------
+    gather = None
+    if world > 1:
+        from isp_tts_b200 import sharding
+        dur_dev = step_resident()
+        gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sharding.gather_durations(dur_dev, t2max=T2, counts=[B] * world)           # warm-up (NCCL communicator, buffers)
+        gs_.record()
+        full = sharding.gather_durations(dur_dev, t2max=T2, counts=[B] * world)
+        ge_.record()
+        torch.cuda.synchronize()
+        frames = torch.tensor([int(ml.sum())], dtype=torch.int64, device=dev)
+        dist.all_reduce(frames)
+        if tuple(full.shape) != (world * B, T2) or int(full.sum()) != int(frames.item()) or not torch.equal(full[rank * B:(rank + 1) * B], dur_dev):
+            raise RuntimeError("gathered durations do not match the ranks' own")
+        gather = {"collective": "ncclAllGather of durations (B_local, T2max) int64 via torch.distributed", "ms": gs_.elapsed_time(ge_),
+                  "bytes_per_rank": int(dur_dev.numel() * 8), "shape": list(full.shape)}
+
     # ---- next row: backward of the log-likelihood, measured beside the hot path ----------
     bwd = None
     if rank == 0 and not args.no_backward:
@@ -511,7 +530,7 @@ def run_ours(args, w):
                 "api": ("isp_stage_operands (valid rows only over PCIe) + " if args.e2e_copy == "staged" else "")
                        + "isp_loglik_forward + isp_mas_forward through isp_tts_b200 (pinned host Q, K, lengths in; durations out); "
                        "the next step's H2D overlaps this step's kernels (two device buffers, one copy stream)"},
-        "next_rows": bwd,
+        "next_rows": bwd, "durations_gather": gather,
         "gpu_launches": 2 * args.steps,
         "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
     }
