@@ -413,6 +413,19 @@ def run_ours(args, w):
             raise RuntimeError("binarization loss from the path differs from the dense formula")
         bwd["f-3 binarization loss"] = {"isp_bin_loss_sums_ms": float(np.mean(t_ours)), "torch_dense_mask_ms": float(np.mean(t_ref)),
                                         "value": float(l1)}
+        # f-3: MAS for consumers that take the path: no dense attn_hard (isp_mas_forward_path with attn_hard == NULL)
+        t_d, t_p = [], []
+        for it in range(8):
+            ev[0].record()
+            mas_forward(logits_b, tl_dev, ml_dev, return_path=True)
+            ev[1].record()
+            mas_forward(logits_b, tl_dev, ml_dev, return_path=True, dense=False)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                t_d.append(ev[0].elapsed_time(ev[1])); t_p.append(ev[1].elapsed_time(ev[2]))
+        bwd["f-3 MAS without the dense output"] = {"isp_mas_forward_path_ms": float(np.mean(t_d)), "attn_hard_null_ms": float(np.mean(t_p)),
+                                                   "bytes_not_written": 2 * B * T1 * T2}
         # f-3: length regulator from the path vs the reference's matmul with a (T1 x T2) 0/1 matrix (temporal_adaptor.py:420-431)
         from isp_tts_b200.consumers import length_regulate
         enc_dim = 384                                   # recipes/acoustic/core.yaml: encoder dim

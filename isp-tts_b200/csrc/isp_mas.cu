@@ -979,7 +979,8 @@ static int launch_one(const MasMaps& maps, const MasParams& p, const MasPlan& pl
 int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
                 const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                 int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    if (!logp || !text_len || !mel_len || !attn_hard || !ws) { set_error("isp_mas_forward: null pointer"); return ISP_ERR_INVALID; }
+    if (!logp || !text_len || !mel_len || !ws) { set_error("isp_mas_forward: null pointer"); return ISP_ERR_INVALID; }
+    if (!attn_hard && !path) { set_error("isp_mas_forward: attn_hard may be NULL only when the path is returned (isp_mas_forward_path)"); return ISP_ERR_INVALID; }
     if (B <= 0 || T1max <= 0 || T2max <= 0) { set_error("isp_mas_forward: B, T1max, T2max must be positive"); return ISP_ERR_INVALID; }
     if (sT2 != 1) { set_error("isp_mas_forward: sT2 must be 1 (token axis contiguous), got %lld", (long long)sT2); return ISP_ERR_INVALID; }
     if (sT1 < T2max || (B > 1 && sB < int64_t(T1max - 1) * sT1 + T2max)) { set_error("isp_mas_forward: overlapping strides"); return ISP_ERR_INVALID; }
@@ -1008,6 +1009,7 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
     p.path_fill = path ? 1 : 0;
     p.ns = pl.ns; p.slots = pl.slots; p.nstg = pl.nstg; p.wlast = pl.wlast;
     p.slot_bytes = int(pl.slot_bytes); p.dbg = g_opt_dbg;
+    if (!attn_hard) p.dbg |= 1 | 4;      // no dense output: neither its zero fill nor the path's ones (the path itself is returned)
     MasMaps maps;
     memset(&maps, 0, sizeof(maps));
     p.tma = (!g_opt_no_tma && make_maps(&maps, logp, sB, sT1, B, T1max, T2max)) ? 1 : 0;

@@ -32,14 +32,15 @@ def _as_len(t, device, name):
 
 
 def mas_forward(attn_logits: torch.Tensor, text_len, mel_len, *, attn_out: torch.Tensor | None = None,
-                durations: bool = True, check_lengths: bool = False, return_path: bool = False):
+                durations: bool = True, check_lengths: bool = False, return_path: bool = False, dense: bool = True):
     """MAS + hard path + durations in one launch.
 
     attn_logits (B, T1max, T2max) fp32 CUDA tensor (rows = mel frames); not modified.
     text_len = in_lens, mel_len = out_lens (int64).  Returns (attn_hard int16
     (B, T1max, T2max), durations int64 (B, T2max) or None).  Enqueued on the
     current stream; no host synchronisation unless check_lengths=True.  With return_path=True a third
-    value follows: the path as one token index per frame, int16 (B, T1max), -1 past mel_len.
+    value follows: the path as one token index per frame, int16 (B, T1max), -1 past mel_len.  dense=False (with
+    return_path=True) skips the dense attn_hard altogether -- the first returned value is then None.
     """
     if attn_logits.dim() != 3:
         raise ValueError("attn_logits must be (B, T1max, T2max)")
@@ -56,7 +57,11 @@ def mas_forward(attn_logits: torch.Tensor, text_len, mel_len, *, attn_out: torch
     ml = _as_len(mel_len, dev, "mel_len")
     if tl.numel() != B or ml.numel() != B:
         raise ValueError("text_len / mel_len must have one entry per utterance")
-    if attn_out is None:
+    if not dense:
+        if not return_path or attn_out is not None:
+            raise ValueError("dense=False needs return_path=True and no attn_out")
+        hard = None
+    elif attn_out is None:
         hard = torch.empty((B, T1, T2), dtype=torch.int16, device=dev)
     else:
         hard = attn_out
@@ -70,7 +75,8 @@ def mas_forward(attn_logits: torch.Tensor, text_len, mel_len, *, attn_out: torch
         path = torch.empty((B, T1), dtype=torch.int16, device=dev) if return_path else None
         if return_path:
             rc = lib.isp_mas_forward_path(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), tl.data_ptr(), ml.data_ptr(),
-                                          B, T1, T2, hard.data_ptr(), dur.data_ptr() if dur is not None else None,
+                                          B, T1, T2, hard.data_ptr() if hard is not None else None,
+                                          dur.data_ptr() if dur is not None else None,
                                           path.data_ptr(), ws.data_ptr(), ws_bytes, stream)
         else:
             rc = lib.isp_mas_forward(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), tl.data_ptr(), ml.data_ptr(),

@@ -307,3 +307,20 @@ def test_temporal_averager_from_durations(cuda_device):
     assert torch.allclose(out.double(), exact, rtol=1e-6, atol=1e-4)
     assert torch.allclose(out, reference(x), rtol=1e-3, atol=0.5)       # the fp32 running sums reach ~1e5 here
     assert (out.masked_select(dur[:, None, :].expand(B, C, T2) == 0) == 0).all()
+
+
+@pytest.mark.parametrize("T2", [72, 200])
+def test_path_only_without_dense_output(cuda_device, T2):
+    """isp_mas_forward_path with attn_hard == NULL: same path and durations as the run that also writes the dense tensor."""
+    B, T1 = 9, 260
+    x = synth.noise_logits(B, T1, T2, 61, quantize=0.5)
+    tl, ml = synth.lengths(B, T2, T1, True, 62)
+    xt = torch.from_numpy(x).to(cuda_device)
+    hard, dur, path = mas_forward(xt, torch.from_numpy(tl), torch.from_numpy(ml), return_path=True)
+    none, dur2, path2 = mas_forward(xt, torch.from_numpy(tl), torch.from_numpy(ml), return_path=True, dense=False)
+    assert none is None and torch.equal(dur, dur2) and torch.equal(path, path2)
+    # the path is the dense tensor's argmax on valid frames
+    for b in range(B):
+        assert torch.equal(hard[b, :ml[b]].argmax(dim=1).to(torch.int16), path[b, :ml[b]])
+    with pytest.raises(ValueError):
+        mas_forward(xt, torch.from_numpy(tl), torch.from_numpy(ml), dense=False)
