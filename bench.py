@@ -202,6 +202,9 @@ def run_ours(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.stage_ctas:
+        from isp_tts_b200 import _lib as _l
+        _l.set_option("stage.ctas", args.stage_ctas)
     if args.mas_ring or args.mas_slots:
         from isp_tts_b200 import _lib
         _lib.set_option("mas.ring_rows", args.mas_ring)
@@ -562,6 +565,7 @@ def main():
     ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--mas-ring", type=int, default=0, help="tuning: MAS logit rows in flight, 0 = heuristic")
     ap.add_argument("--mas-slots", type=int, default=0, help="tuning: utterances per CTA (1|2), 0 = heuristic")
+    ap.add_argument("--stage-ctas", type=int, default=0, help="tuning: CTAs of the host->device staging kernel, 0 = default")
     ap.add_argument("--no-backward", action="store_true", help="skip the f-1 backward measurement that follows the timed steps")
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (cfg5 sweep: 64..4096 with the cfg3 length law); 0 = the workload's own")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],

@@ -4,8 +4,10 @@
 //
 // The reference moves whole padded batches with tensor.to(device) (tts/train.py -> trainer: batch.to(device)); with
 // LJSpeech-shaped lengths 40 % of those bytes are padding.  A plain gather kernel reads the pinned host tensors through
-// their device-visible (UVA) addresses: 16 B per lane, eight loads in flight per thread, eight CTAs (PCIe is saturated by any grid from 8 CTAs up: 51 GB/s against 54 GB/s for the DMA of the padded tensors) so that it can
-// run on a copy stream next to the previous step's kernels without taking their SMs.
+// their device-visible (UVA) addresses: 16 B per lane, eight loads in flight per thread.  Alone, any grid from 8 CTAs up
+// saturates the link (51 GB/s against 54 GB/s for the DMA of the padded tensors); next to the previous step's kernels,
+// which is where it runs, a CTA only gets the issue slots and memory pipes its SM has left, and one CTA per SM is what
+// keeps the link busy (end to end at cfg3: 8 CTAs 1.39 ms/step, 32: 1.05, 148: 1.00).
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -84,7 +86,7 @@ int stage_operands(const void* q_host, const void* k_host, int dtype, const int6
         dev_ptr[i] = at.devicePointer;
     }
     const int vpr = int(size_t(D) * elem / 16);
-    stage_operands_kernel<<<g_opt_stage_ctas > 0 ? g_opt_stage_ctas : 8, kStageThreads, 0, stream>>>(static_cast<const uint4*>(dev_ptr[0]), static_cast<const uint4*>(dev_ptr[1]),
+    stage_operands_kernel<<<g_opt_stage_ctas > 0 ? g_opt_stage_ctas : 148, kStageThreads, 0, stream>>>(static_cast<const uint4*>(dev_ptr[0]), static_cast<const uint4*>(dev_ptr[1]),
                                                            text_len, mel_len, static_cast<uint4*>(q_dev), static_cast<uint4*>(k_dev),
                                                            B, T1max, T2max, vpr);
     cudaError_t e = cudaGetLastError();
