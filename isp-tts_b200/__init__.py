@@ -15,6 +15,9 @@ _LAZY = {
     "ConvAttention": "alignment", "ConvAttentionConfig": "alignment", "ConvBlock1D": "alignment",
     "batch_diagonal_prior": "alignment", "loglik_forward": "alignment",
     "b_mas": "mas", "cuda_b_mas": "mas", "mas_forward": "mas", "mas_durations": "mas",
+    "binarization_loss": "mas", "stage_operands": "alignment",
+    "LengthRegulator": "consumers", "TemporalAverager": "consumers", "length_regulate": "consumers", "temporal_average": "consumers",
+    "AttentionCTCLoss": "ctc", "attention_ctc_loss": "ctc", "ctc_nll": "ctc",
     "gather_durations": "sharding", "shard_bounds": "sharding", "balanced_assignment": "sharding",
 }
 
