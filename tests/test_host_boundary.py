@@ -58,6 +58,24 @@ def test_no_cpu_fallback():
             al(torch.randn(1, 8, 4), torch.randn(1, 8, 3), torch.tensor([4]), torch.tensor([3]))
 
 
+def test_no_cpu_fallback_in_the_rows_either_side_of_the_path():
+    """The consumers of the path, the forward-sum loss and the staging helper raise on CPU tensors as well."""
+    from isp_tts_b200 import (AttentionCTCLoss, LengthRegulator, TemporalAverager, binarization_loss, stage_operands)
+    tl, ml = torch.tensor([3]), torch.tensor([4])
+    with pytest.raises(_lib.IspError):
+        AttentionCTCLoss()(torch.zeros(1, 4, 3), tl, ml)
+    with pytest.raises(_lib.IspError):
+        TemporalAverager()(torch.zeros(1, 1, 4), torch.tensor([[2, 1, 1]]))
+    with pytest.raises(_lib.IspError):
+        LengthRegulator()(torch.zeros(1, 3, 8), torch.tensor([[2, 1, 1]]), path=torch.zeros(1, 4, dtype=torch.int16))
+    with pytest.raises(_lib.IspError):
+        LengthRegulator()(torch.zeros(1, 3, 8), torch.tensor([[2, 1, 1]]))           # no dense fallback either
+    with pytest.raises(_lib.IspError):
+        binarization_loss(torch.zeros(1, 4, 3), torch.zeros(1, 4, dtype=torch.int16), ml)
+    with pytest.raises(_lib.IspError):
+        stage_operands(torch.zeros(1, 4, 8), torch.zeros(1, 3, 8), tl, ml)
+
+
 def test_shard_bounds_cover_the_batch():
     for n in (0, 1, 7, 8, 256, 4097):
         for world in (1, 2, 3, 8):
