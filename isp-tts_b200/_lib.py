@@ -85,7 +85,8 @@ def check(rc: int, what: str):
 
 def set_option(key: str, value: int) -> int:
     rc = load().isp_set_option(key.encode(), int(value))
-    if rc == -1 and key not in ("mas.cols_per_lane", "mas.ring_rows", "mas.slots", "mas.dbg", "mas.bits_global", "mas.no_tma", "loglik.debug_scores", "stage.ctas"):
+    if rc == -1 and key not in ("mas.cols_per_lane", "mas.ring_rows", "mas.slots", "mas.dbg", "mas.bits_global", "mas.no_tma", "mas.impl",
+                               "mas2.min_pair_stages", "mas2.single", "mas2.fill_us", "mas2.together", "mas2.pace", "loglik.debug_scores", "stage.ctas"):
         raise IspError(f"unknown option {key!r}")
     return rc
 

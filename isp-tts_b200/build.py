@@ -15,8 +15,8 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 SO_PATH = os.path.join(PKG_DIR, "libisp_tts_b200.so")
-SOURCES = ["isp_capi.cu", "isp_mas.cu", "isp_loglik.cu", "isp_loglik_bwd.cu", "isp_consumers.cu", "isp_stage.cu", "isp_ctc.cu"]
-HEADERS = ["common.cuh", "isp_internal.h", os.path.join("..", "..", "include", "isp_tts_b200.h")]
+SOURCES = ["isp_capi.cu", "isp_mas.cu", "isp_mas2.cu", "isp_loglik.cu", "isp_loglik_bwd.cu", "isp_consumers.cu", "isp_stage.cu", "isp_ctc.cu"]
+HEADERS = ["common.cuh", "isp_internal.h", "isp_mas_ptx.cuh", os.path.join("..", "..", "include", "isp_tts_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -59,7 +59,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stdout + r.stderr))
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs
+    # the CUDA runtime is linked dynamically (torch has already loaded libcudart.so.12 into the process; the
+    # rpath covers a bare ctypes load): the static runtime would embed every runtime entry point in the library
+    cmd = [nvcc, "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -1,6 +1,7 @@
 // C ABI (include/isp_tts_b200.h): argument checks, error strings, dispatch.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "isp_internal.h"
 
@@ -66,11 +67,25 @@ int isp_bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t
 
 int isp_mas_status(const void* ws, void* stream) {
     if (!ws) { isp::set_error("isp_mas_status: null workspace"); return -1; }
-    int v = -1;
-    cudaError_t e = cudaMemcpyAsync(&v, ws, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
-    if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    int v[2] = {-1, 0};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(v, ws, sizeof(v), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { isp::cuda_fail(e, "isp_mas_status"); return -1; }
-    return v;
+    if (v[0] != -2) return v[0];                        // isp_mas.cu: a counter
+    // isp_mas2.cu: one flag per utterance behind the order array (see mas2_workspace_bytes)
+    const int B = v[1];
+    if (B <= 0) return -1;
+    unsigned char* flags = static_cast<unsigned char*>(malloc(size_t(B)));
+    if (!flags) return -1;
+    const char* src = static_cast<const char*>(ws) + 256 + ((size_t(B) * 4 + 15) & ~size_t(15));
+    e = cudaMemcpyAsync(flags, src, size_t(B), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    int bad = 0;
+    if (e == cudaSuccess) for (int i = 0; i < B; ++i) bad += flags[i] != 0;
+    free(flags);
+    if (e != cudaSuccess) { isp::cuda_fail(e, "isp_mas_status"); return -1; }
+    return bad;
 }
 
 size_t isp_loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype) {

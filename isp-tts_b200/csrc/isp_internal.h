@@ -20,6 +20,13 @@ int    mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
 int    bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t* mel_len, int B, int T1max, int T2max,
                      float eps, float* sums, cudaStream_t stream);
 int    mas_set_option(const char* key, int value, int* prev);
+// second MAS kernel (isp_mas2.cu): T2max <= 256, backpointer words in shared memory
+bool   mas2_supported(int B, int T1max, int T2max);
+size_t mas2_workspace_bytes(int B);
+int    mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text_len, const int64_t* mel_len,
+                    int B, int T1max, int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws,
+                    int no_tma, int ring_rows, int slots, int dbg, cudaStream_t stream);
+int    mas2_set_option(const char* key, int value, int* prev);
 
 size_t loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,

@@ -66,6 +66,7 @@
 
 #include "common.cuh"
 #include "isp_internal.h"
+#include "isp_mas_ptx.cuh"
 
 namespace isp {
 
@@ -108,123 +109,8 @@ struct MasParams {
 
 struct MasMaps { CUtensorMap m[kNumBox]; };
 
-// ---- small PTX helpers ---------------------------------------------------------------
-ISP_DEVINL void tma_load_box(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
-        : "memory");
-}
-ISP_DEVINL int ld_volatile_sa(uint32_t saddr) {
-    int v;
-    asm volatile("ld.volatile.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-    return v;
-}
-// predicated forms: a divergent `if (lane == ...)` around one instruction costs BSSY/BSYNC and a branch.  The counter
-// stores are plain st.shared inside `asm volatile` (the compiler keeps their place; st.volatile would add a MEMBAR)
-ISP_DEVINL void mbar_arrive_if_sa(uint32_t bar, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 st;\n\tsetp.ne.u32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
-                 ::"r"(bar), "r"(uint32_t(pred)) : "memory");
-}
-ISP_DEVINL void st_volatile_if_sa(uint32_t saddr, int v, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared::cta.s32 [%0], %1;\n\t}"
-                 ::"r"(saddr), "r"(v), "r"(uint32_t(pred)) : "memory");
-}
-ISP_DEVINL void sts_f32_if(uint32_t saddr, float v, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}"
-                 ::"r"(saddr), "f"(v), "r"(uint32_t(pred)) : "memory");
-}
-ISP_DEVINL void stg_u16_if(int16_t* gp, int v, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u16 [%0], %1;\n\t}" ::"l"(gp), "h"(short(v)), "r"(uint32_t(pred)) : "memory");
-}
-ISP_DEVINL void stg_s64_if(int64_t* gp, int64_t v, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.s64 [%0], %1;\n\t}" ::"l"(gp), "l"(v), "r"(uint32_t(pred)) : "memory");
-}
-ISP_DEVINL void sts_u64(uint32_t saddr, uint32_t lo, uint32_t hi) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(lo), "r"(hi) : "memory");
-}
-ISP_DEVINL void st_volatile_sa(uint32_t saddr, int v) {
-    asm volatile("st.shared::cta.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-ISP_DEVINL void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-}
-ISP_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-ISP_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-ISP_DEVINL void cp_async4(uint32_t sdst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
-}
-ISP_DEVINL void cp_async_arrive_noinc_sa(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-ISP_DEVINL void mbar_arrive_sa(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-ISP_DEVINL void mbar_expect_tx_sa(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-}
-ISP_DEVINL uint32_t mbar_test_sa(uint32_t bar, uint32_t parity) {     // non-blocking
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok;
-}
-ISP_DEVINL uint32_t mbar_try_sa(uint32_t bar, uint32_t parity) {      // may sleep in hardware
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok;
-}
-// the loaders' wait: sleeps in hardware (up to ~1 us per try) instead of spinning on an issue port a strip warp needs
-ISP_DEVINL void mbar_wait_idle_sa(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000u) : "memory");
-        if (++spins > (1u << 24)) __trap();
-    } while (!ok);
-}
-// spin with a watchdog: a protocol bug must surface as a launch failure, not as a hung GPU
-ISP_DEVINL void mbar_wait_sa(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_sa(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
-}
-ISP_DEVINL float set_ge(float a, float b) {   // 1.0f if a >= b (false on NaN), else 0.0f: one FSET
-    float d;
-    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-}
 ISP_DEVINL void lds_row(float (&x)[kC], uint32_t saddr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(saddr));
-}
-ISP_DEVINL float lds_f32(uint32_t saddr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
-    return v;
-}
-ISP_DEVINL void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
-ISP_DEVINL void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
-ISP_DEVINL uint4 lds_v4(uint32_t saddr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-    return v;
-}
-ISP_DEVINL void st_release_sa(uint32_t saddr, int v) {
-    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-ISP_DEVINL int ld_acquire_sa(uint32_t saddr) {
-    int v;
-    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-    return v;
-}
-
-// one backtrack row on a one-hot position: stay where A is 0, move one column down where A is 1.
-// Written as two LOP3 levels so that the dependent chain is 2 ALU ops per row, not 3.
-ISP_DEVINL uint32_t bt_step(uint32_t R, uint32_t A, uint32_t A1) {
-    uint32_t P, Rs = R >> 1, out;
-    asm("lop3.b32 %0, %1, %2, 0, 0x30;" : "=r"(P) : "r"(R), "r"(A));              // R & ~A
-    asm("lop3.b32 %0, %1, %2, %3, 0xf8;" : "=r"(out) : "r"(P), "r"(Rs), "r"(A1));   // P | (Rs & A1)
-    return out;
 }
 
 // ---- one DP row for one lane --------------------------------------------------------
@@ -838,6 +724,7 @@ static int g_opt_dbg = 0;
 static int g_opt_bits_global = 0;
 static int g_opt_no_tma = 0;
 static int g_opt_cols = 0;     // accepted for compatibility with older tools; the kernel has one strip width
+static int g_opt_impl = 0;     // 0: isp_mas2.cu where it covers the shape, 1: always this file's kernel, 2: isp_mas2.cu or fail
 
 int mas_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas.ring_rows")) { *prev = g_opt_ring_rows; g_opt_ring_rows = value; return 0; }
@@ -846,7 +733,8 @@ int mas_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas.bits_global")) { *prev = g_opt_bits_global; g_opt_bits_global = value; return 0; }
     if (!strcmp(key, "mas.no_tma")) { *prev = g_opt_no_tma; g_opt_no_tma = value; return 0; }
     if (!strcmp(key, "mas.cols_per_lane")) { *prev = g_opt_cols; g_opt_cols = value; return 0; }
-    return -1;
+    if (!strcmp(key, "mas.impl")) { *prev = g_opt_impl; g_opt_impl = value; return 0; }
+    return mas2_set_option(key, value, prev);
 }
 
 struct MasPlan {
@@ -960,7 +848,9 @@ static bool make_maps(MasMaps* maps, const float* logp, int64_t sB, int64_t sT1,
 size_t mas_workspace_bytes(int B, int T1max, int T2max) {
     if (B <= 0 || T1max <= 0 || T2max <= 0) return 0;
     const int ns = (T2max + kW - 1) / kW;
-    return 256 + size_t(B) * bits_words_for(T1max, ns) * 4 + ((size_t(B) * T1max * 2 + 15) & ~size_t(15));
+    const size_t v1 = 256 + size_t(B) * bits_words_for(T1max, ns) * 4 + ((size_t(B) * T1max * 2 + 15) & ~size_t(15));
+    const size_t v2 = mas2_workspace_bytes(B);
+    return v1 > v2 ? v1 : v2;
 }
 
 template <bool BS, bool MULTI>
@@ -992,6 +882,11 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
         set_error("isp_mas_forward: workspace too small or not 16 B aligned (%zu < %zu)", ws_bytes, mas_workspace_bytes(B, T1max, T2max));
         return ISP_ERR_WORKSPACE;
     }
+    const bool want2 = g_opt_impl != 1 && !g_opt_bits_global && g_opt_slots != 3;
+    if (want2 && mas2_supported(B, T1max, T2max))
+        return mas2_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws,
+                            g_opt_no_tma, g_opt_ring_rows, g_opt_slots, g_opt_dbg, stream);
+    if (g_opt_impl == 2) { set_error("isp_mas_forward: mas.impl=2 but T1max=%d T2max=%d is outside isp_mas2.cu's range", T1max, T2max); return ISP_ERR_UNSUPPORTED; }
     MasPlan pl;
     int rc = mas_plan(B, T1max, T2max, &pl);
     if (rc) { set_error("isp_mas_forward: no kernel configuration for T1max=%d T2max=%d", T1max, T2max); return rc; }

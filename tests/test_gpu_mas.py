@@ -34,14 +34,18 @@ def assert_same(hard, dur, ref_hard, ref_dur, what=""):
 @pytest.fixture(autouse=True)
 def _reset_options():
     yield
-    for key in ("mas.ring_rows", "mas.slots", "mas.bits_global", "mas.no_tma"):
+    for key in ("mas.ring_rows", "mas.slots", "mas.bits_global", "mas.no_tma", "mas.impl", "mas.dbg", "mas2.min_pair_stages", "mas2.single", "mas2.together", "mas2.fill_us"):
         _lib.set_option(key, 0)
+    _lib.set_option("mas2.pace", -1)
 
 
-# kernel variants: backpointer bits in shared memory or in the workspace, tiled TMA or 4 B async copies,
-# one or two utterances per CTA
-MODES = {"auto": {}, "three_slots": {"mas.slots": 3}, "bits_global": {"mas.bits_global": 1}, "no_tma": {"mas.no_tma": 1},
-         "two_slots": {"mas.slots": 2}, "two_slots_global_no_tma": {"mas.slots": 2, "mas.bits_global": 1, "mas.no_tma": 1}}
+# kernel variants.  isp_mas2.cu (the default up to 256 tokens): tiled TMA or 4 B async copies, one utterance per CTA,
+# pairs side by side, pairs one after the other.  isp_mas.cu (wider utterances, or mas.impl = 1): backpointer bits in shared
+# memory or in the workspace, one to three utterances per CTA.
+MODES = {"auto": {}, "unpaced_pairs": {"mas2.pace": 0, "mas.slots": 2}, "no_tma": {"mas.no_tma": 1}, "one_slot": {"mas.slots": 1}, "two_slots": {"mas.slots": 2},
+         "pairs_in_turn": {"mas.slots": 2, "mas2.min_pair_stages": 64}, "two_slots_no_tma": {"mas.slots": 2, "mas.no_tma": 1},
+         "v1": {"mas.impl": 1}, "v1_three_slots": {"mas.impl": 1, "mas.slots": 3}, "v1_bits_global": {"mas.impl": 1, "mas.bits_global": 1},
+         "v1_two_slots_global_no_tma": {"mas.impl": 1, "mas.slots": 2, "mas.bits_global": 1, "mas.no_tma": 1}}
 
 
 def set_mode(mode):
@@ -103,7 +107,7 @@ def test_small_ring_wraparound(cuda_device, ring):
     x = synth.noise_logits(9, 257, 132, 5, quantize=0.25)
     tl, ml = synth.lengths(9, 132, 257, True, 5)
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
-    for mode in ("auto", "no_tma", "two_slots"):
+    for mode in ("auto", "unpaced_pairs", "no_tma", "two_slots", "v1", "pairs_in_turn"):
         set_mode(mode)
         _lib.set_option("mas.ring_rows", ring)
         hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
@@ -203,7 +207,7 @@ def test_cpu_tensor_is_rejected():
         mas_forward(torch.zeros(1, 4, 4), torch.tensor([4]), torch.tensor([4]))
 
 
-@pytest.mark.parametrize("T2,mode", [(72, "auto"), (72, "bits_global"), (160, "auto"), (160, "bits_global"), (160, "no_tma")])
+@pytest.mark.parametrize("T2,mode", [(72, "auto"), (72, "v1_bits_global"), (160, "auto"), (160, "v1"), (160, "no_tma"), (160, "pairs_in_turn")])
 def test_slots_take_several_utterances(cuda_device, T2, mode):
     """More utterances than 2 x #SMs (the cfg5 sweep's regime): every persistent slot aligns several utterances
     in a row, with one strip (72 tokens) or two (160), bits in shared memory or in the workspace."""
