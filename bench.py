@@ -11,7 +11,7 @@ owns its own batch (sharded by utterance, no collective on the data path): weak 
 Keys beyond the base contract:
   roofline      the dominant kernel of the step, timed live with CUDA events
   kernels       per-kernel time / algorithmic bytes / fraction of the measured HBM peak
-  cpu_baseline  the oracle port (torch-CPU log-likelihood + C/OpenMP MAS) on a bounded sample
+  cpu_baseline  the reference's CPU route on the whole batch: torch-CPU log-likelihood ops + its own numba b_mas (oracle/_ref)
   e2e           same metric through the public API with pinned HOST buffers (H2D + D2H timed)
 """
 from __future__ import annotations
@@ -115,67 +115,125 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port on the host cores
+# reference arm / CPU baseline: the reference's own CPU route on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_step(q, k, tl, ml, scale, nthreads=0):
-    """One hot-path pass on the CPU: reference op sequence in torch-CPU + the C/OpenMP MAS."""
-    import torch
-    from oracle import loglik_torch as olt
-    from oracle import mas as omas
-    soft, logits = olt.loglik(q, k, tl, ml, scale)
-    hard, dur = omas.b_mas_with_durations(logits.numpy(), tl.numpy(), ml.numpy(), nthreads)
-    return dur
+def base_config(w, tl, ml):
+    return {"workload": w.name, "batch_per_gpu": w.batch, "t_text_max": w.t2max, "t_mel_max": w.t1max, "attention_dim": w.dim,
+            "ragged": w.ragged, "valid_cells_per_batch": int((tl * ml).sum()), "padded_cells_per_batch": w.batch * w.t1max * w.t2max}
 
 
-def cpu_baseline(w, sample_utts, reps, warm=1):
+class CpuPath:
+    """The hot path as the reference runs it on a CPU (alignment.py:189-208, 305-312, 275): the log-likelihood op sequence in
+    torch (the reference has no separately callable function for it: it is inline in ConvAttention.forward, so
+    oracle/loglik_torch.py restates it op by op), then the reference's OWN numba `b_mas`, unmodified, from oracle/_ref
+    (falls back to the C/OpenMP port, and says so, only if that cannot be loaded), then attn_hard.sum(dim=1)."""
+
+    def __init__(self):
+        import torch
+        from oracle import ref_mas
+        self.ncores = os.cpu_count() or 1
+        torch.set_num_threads(self.ncores)           # every host core, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+        self.b_mas, self.why = ref_mas.load()
+        self.kind = "reference" if self.b_mas is not None else "port"
+        self.mas_threads = self.ncores
+        if self.b_mas is not None:
+            import numba
+            try:
+                numba.set_num_threads(min(self.ncores, numba.config.NUMBA_NUM_THREADS))
+            except Exception:
+                pass
+            self.mas_threads = int(numba.get_num_threads())
+
+    def mas(self, logits_np, tl_np, ml_np, threads=None):
+        if self.b_mas is not None:
+            if threads is not None:
+                import numba
+                numba.set_num_threads(threads)
+            try:
+                return self.b_mas(logits_np, tl_np, ml_np)            # mutates logits_np (SURVEY.md A.3): callers pass a scratch copy
+            finally:
+                if threads is not None:
+                    import numba
+                    numba.set_num_threads(self.mas_threads)
+        from oracle import mas as omas
+        return omas.b_mas_with_durations(logits_np, tl_np, ml_np, threads or self.ncores)[0]
+
+    def step(self, q, k, tl, ml, scale):
+        from oracle import loglik_torch as olt
+        soft, logits = olt.loglik(q, k, tl, ml, scale)
+        hard = self.mas(logits.numpy(), tl.numpy(), ml.numpy())
+        return hard.sum(axis=1, dtype=np.int64)                        # alignment.py:275
+
+    def describe(self, w, n):
+        what = ("the reference's numba b_mas (tts/modules/aligner/mas.py:30-35, unmodified, staged in oracle/_ref)" if self.kind == "reference"
+                else f"C/OpenMP port of b_mas (oracle/mas_oracle.c) because: {self.why}")
+        whole = "the whole batch" if n == w.batch else f"first {n} of {w.batch} utterances"
+        return f"{whole} of {w.name}; fp32; torch-CPU log-likelihood ops (alignment.py:189-208 sequence, {self.ncores} threads) + {what} on {self.mas_threads} threads"
+
+
+def cpu_inputs(w, n):
     import torch
     from isp_tts_b200 import synth
-    from oracle import mas as omas
     tl, ml = synth.workload_lengths(w)
-    n = min(sample_utts, w.batch)
     tl, ml = tl[:n].copy(), ml[:n].copy()
     q, k = synth.encoded_pair(n, w.t1max, w.t2max, w.dim, tl, ml, w.seed + 1)
-    qt, kt, tlt, mlt = torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(tl), torch.from_numpy(ml)
+    return torch.from_numpy(q), torch.from_numpy(k), torch.from_numpy(tl), torch.from_numpy(ml), tl, ml
+
+
+def cpu_baseline(w, reps, warm=1, budget_s=25.0):
+    """Timed on the WHOLE batch of the workload (a cfg3 step is ~0.2 s of host time) unless one pass would blow the budget."""
+    cpu = CpuPath()
+    n = w.batch
+    qt, kt, tlt, mlt, tl, ml = cpu_inputs(w, n)
     scale = w.dim ** -0.5
-    # every host core, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)
-    ncores = os.cpu_count() or 1
-    torch.set_num_threads(ncores)
-    for _ in range(warm):
-        cpu_step(qt, kt, tlt, mlt, scale, ncores)
+    t0 = time.perf_counter()
+    cpu.step(qt, kt, tlt, mlt, scale)                                   # warm-up: numba JIT (~20 s the first time), torch threads
+    first = time.perf_counter() - t0
+    for _ in range(max(0, warm - 1)):
+        cpu.step(qt, kt, tlt, mlt, scale)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_step(qt, kt, tlt, mlt, scale, ncores)
+        cpu.step(qt, kt, tlt, mlt, scale)
         times.append(time.perf_counter() - t0)
+        if sum(times) > budget_s:
+            break
     best = min(times)
-    cores = ncores
-    return {
-        "value": n / best, "unit": UNIT, "cores": int(cores), "kind": "port",
-        "sample": f"first {n} of {w.batch} utterances of {w.name}; fp32; best of {reps} "
-                  f"(median {n / float(np.median(times)):.1f}); torch-CPU log-likelihood ops "
-                  f"(alignment.py:189-208 sequence) + C/OpenMP MAS (oracle/mas_oracle.c)",
-        "valid_cells_per_s": float((tl * ml).sum()) / best,
-        "ms_per_sample": best * 1e3,
-    }, times
+    # MAS alone, as SURVEY.md 8d asks: b_mas(x.copy(), ...) with the copy outside the timed region, all threads and one
+    from oracle import loglik_torch as olt
+    logits = olt.loglik(qt, kt, tlt, mlt, scale)[1].numpy()
+    mas_all, mas_one = [], []
+    for _ in range(3):
+        x = logits.copy()
+        t0 = time.perf_counter(); cpu.mas(x, tl, ml); mas_all.append(time.perf_counter() - t0)
+    x = logits.copy()
+    t0 = time.perf_counter(); cpu.mas(x, tl, ml, threads=1); mas_one.append(time.perf_counter() - t0)
+    out = {
+        "value": n / best, "unit": UNIT, "cores": int(cpu.ncores), "kind": cpu.kind, "sample": cpu.describe(w, n) + f"; best of {len(times)} (median {n / float(np.median(times)):.1f}); first call incl. JIT {first:.1f} s",
+        "valid_cells_per_s": float((tl * ml).sum()) / best, "ms_per_step": best * 1e3,
+        "mas_only": {"all_threads_utt_per_s": n / min(mas_all), "threads": cpu.mas_threads, "one_thread_utt_per_s": n / min(mas_one),
+                     "ms_all_threads": min(mas_all) * 1e3},
+    }
+    return out, times, cpu, logits
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each step is a bounded sample of the workload so that K+W steps end within minutes
-    sample = min(w.batch, 32)
-    base, times = cpu_baseline(w, sample, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    base, times, cpu, _ = cpu_baseline(w, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)), budget_s=120.0)
+    from isp_tts_b200 import synth
+    tl, ml = synth.workload_lengths(w)
     med = float(np.median(times))
+    cfg = base_config(w, tl, ml)
+    cfg["step"] = "one pass of the hot path over the whole batch on the host cores (the reference's CPU route)"
     out = {
-        "impl": "reference", "metric": METRIC, "value": sample / med, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "batch_per_gpu": w.batch, "t_text_max": w.t2max, "t_mel_max": w.t1max,
-                   "attention_dim": w.dim, "step": f"CPU port on a {sample}-utterance sample per step"},
-        "cpu_baseline": {"value": sample / med, "unit": UNIT, "cores": base["cores"], "kind": "port",
-                         "sample": base["sample"]},
-        "e2e": {"value": sample / med, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": w.batch / med, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": w.batch / med, "unit": UNIT, "cores": base["cores"], "kind": base["kind"], "sample": base["sample"],
+                         "mas_only": base["mas_only"]},
+        "e2e": {"value": w.batch / med, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out))
@@ -240,6 +298,7 @@ def run_ours(args, w):
     bufs = [dict(q=torch.empty_like(q_dev), k=torch.empty_like(k_dev), tl=torch.empty_like(tl_dev), ml=torch.empty_like(ml_dev),
                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
     dur_hosts = [torch.empty((B, T2), dtype=torch.int64).pin_memory() for _ in range(2)]
+    hard_hosts = [torch.empty((B, T1, T2), dtype=torch.int16).pin_memory() for _ in range(2)] if args.e2e_outputs == "hard" else None
     state = {"i": 0}
 
     def e2e_upload(slot):
@@ -269,6 +328,8 @@ def run_ours(args, w):
         hard, dur = mas_forward(logits, bf["tl"], bf["ml"])
         bf["free"].record(cur)
         dur_hosts[slot].copy_(dur, non_blocking=True)
+        if hard_hosts is not None:
+            hard_hosts[slot].copy_(hard, non_blocking=True)          # what the reference's CPU route hands back (alignment.py:312)
         state["i"] = i + 1
         return dur_hosts[slot]
 
@@ -499,27 +560,51 @@ def run_ours(args, w):
     by_mas = mas_bytes(tl, ml, B, T1, T2)
     by_ll = loglik_bytes(B, T1, T2, D, elem)
     fl_ll = loglik_flops(B, T1, T2, D)
+    # the log-likelihood kernel only reads operand rows below the lengths, and only runs the MMA on 128-frame tiles that hold a
+    # valid frame: both accountings are reported (SURVEY.md 8d's padded-operand formula, and what really has to move / execute)
+    by_ll_valid = elem * D * int(ml.sum() + tl.sum()) + 8 * B * T1 * T2
+    fl_ll_exec = 2 * D * int(((ml + 127) // 128 * 128).sum()) * ((T2 + 15) // 16 * 16)
+    ncu = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # per-launch DRAM bytes / pipe activity from the committed ncu capture
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                ncu = json.load(f).get(w.name.split(":")[0], {})
+        except Exception:
+            ncu = {}
     kern = {
         "isp_loglik (tcgen05 GEMM + fused epilogue)": {
             "ms": t_loglik, "algorithmic_bytes": by_ll, "gbs": by_ll / t_loglik / 1e6, "hbm_frac": by_ll / t_loglik / 1e6 / hbm_peak,
-            "tflops": fl_ll / t_loglik / 1e9, "tensor_frac": fl_ll / t_loglik / 1e9 / tf_peak},
+            "valid_row_bytes": by_ll_valid, "hbm_frac_valid_rows": by_ll_valid / t_loglik / 1e6 / hbm_peak,
+            "tflops_padded": fl_ll / t_loglik / 1e9, "tflops_executed": fl_ll_exec / t_loglik / 1e9,
+            "tensor_frac_executed": fl_ll_exec / t_loglik / 1e9 / tf_peak,
+            "tensor_pipe_active_ncu": ncu.get("isp_loglik_tensor_pipe_active")},
         "isp_mas (wavefront DP + backtrack + durations)": {
             "ms": t_mas, "algorithmic_bytes": by_mas, "gbs": by_mas / t_mas / 1e6, "hbm_frac": by_mas / t_mas / 1e6 / hbm_peak},
     }
     dom = max(kern, key=lambda n: kern[n]["ms"])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # per-launch DRAM bytes from the committed ncu capture
-    if os.path.exists(tpath):
-        try:
-            with open(tpath) as f:
-                traffic = json.load(f).get(w.name.split(":")[0], {}).get(dom.split(" ")[0])
-        except Exception:
-            traffic = None
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kern[dom]["hbm_frac"], "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)"}
 
-    n_cpu = min(B, 32)
-    cpu = None if args.no_cpu else cpu_baseline(w, n_cpu, reps=3)[0]
+    def roof(name):
+        return {"kernel": name, "bound": "hbm", "achieved": kern[name]["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kern[name]["hbm_frac"],
+                "traffic": ncu.get(name.split(" ")[0]), "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)"}
+    roofline = roof(dom)
+    roofline_all = [roof(n) for n in kern]
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cpu, _, cpu_path, logits_np = cpu_baseline(w, reps=3)
+        # the reference's end-to-end CPU route for MAS on a CUDA tensor (alignment.py:305-312): D2H fp32 + b_mas + H2D int16
+        lg = torch.from_numpy(logits_np).to(dev)
+        tl_np, ml_np = tl.copy(), ml.copy()
+        route = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = torch.from_numpy(cpu_path.mas(lg.detach().cpu().numpy(), tl_np, ml_np)).to(dev)
+            torch.cuda.synchronize()
+            route.append(time.perf_counter() - t0)
+        cpu["reference_cpu_route_mas"] = {"ms": min(route) * 1e3, "what": "attn_logits.cpu().numpy() -> b_mas -> torch.from_numpy(...).to(device) (alignment.py:305-312)"}
+        del lg, out
 
     utts = world * B * args.steps
     valid_cells = float((tl * ml).sum()) * world * args.steps
@@ -532,22 +617,24 @@ def run_ours(args, w):
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16 GEMM operands; f32 accumulate, epilogue and MAS" if elem == 2 else "tf32 GEMM products; f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": w.name, "batch_per_gpu": B, "t_text_max": T2, "t_mel_max": T1, "attention_dim": D,
-                   "ragged": w.ragged, "valid_cells_per_batch": int((tl * ml).sum()), "padded_cells_per_batch": B * T1 * T2,
+        "config": {**base_config(w, tl, ml),
                    "sharding": f"by utterance, {world} rank(s), no collective on the data path",
                    "launch": launch if launch != "graph" else "CUDA graph replay of the step (isp_loglik_forward + isp_mas_forward)",
                    "l2": "per-step working set (operands + 3 dense outputs) = %.0f MB > 126 MB L2; no explicit flush" % (
                        (by_ll + 2 * B * T1 * T2) / 1e6)},
         "valid_cells_per_s": valid_cells / (total_ms / 1e3),
         "padded_cells_per_s": world * B * T1 * T2 * args.steps / (total_ms / 1e3),
-        "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_kernels": roofline_all, "kernels": kern, "cpu_baseline": cpu,
         "e2e": {"value": utts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(dur_host.numel() * 8), "ms_per_step": e2e_ms / args.steps,
+                "d2h_bytes_per_step": int(dur_host.numel() * 8) + (2 * B * T1 * T2 if hard_hosts is not None else 0), "ms_per_step": e2e_ms / args.steps,
                 "api": ("isp_stage_operands (valid rows only over PCIe) + " if args.e2e_copy == "staged" else "")
-                       + "isp_loglik_forward + isp_mas_forward through isp_tts_b200 (pinned host Q, K, lengths in; durations out); "
-                       "the next step's H2D overlaps this step's kernels (two device buffers, one copy stream)"},
+                       + "isp_loglik_forward + isp_mas_forward through isp_tts_b200.  In: pinned host Q, K (already cast to the GEMM's "
+                       + ("bf16" if elem == 2 else "fp32") + " on the host, outside the timed region) and int64 lengths.  Out: the int64 durations"
+                       + (" and the dense int16 attn_hard (the reference's CPU route hands back attn_hard, alignment.py:312)" if hard_hosts is not None
+                          else " only; attn_hard, attn_logits and attn_soft stay on the device (--e2e-outputs hard also brings attn_hard back)")
+                       + ".  The next step's H2D overlaps this step's kernels (two device buffers, one copy stream)"},
         "next_rows": bwd, "durations_gather": gather,
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": (2 + (1 if B > 512 else 0)) * args.steps,      # loglik + MAS (+ the MAS plan kernel beyond 512 utterances)
         "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
     }
     print(json.dumps(out))
@@ -573,6 +660,8 @@ def main():
     ap.add_argument("--e2e-copy", default="staged", choices=["staged", "padded"],
                     help="end-to-end H2D of Q and K: isp_stage_operands (valid rows only) or plain copies of the padded tensors")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (sweeps)")
+    ap.add_argument("--e2e-outputs", default="durations", choices=["durations", "hard"],
+                    help="what the end-to-end leg reads back: the durations (default) or the durations and the dense attn_hard")
     args = ap.parse_args()
     from isp_tts_b200 import synth
     w = synth.WORKLOADS[args.workload]

@@ -48,6 +48,13 @@
 #include "isp_internal.h"
 #include "isp_mas_ptx.cuh"
 
+#ifndef ISP_MAS2_SHFL
+#define ISP_MAS2_SHFL 0
+#endif
+#ifndef ISP_MAS2_ABL
+#define ISP_MAS2_ABL 0          // micro-benchmark only (tools/ubench/step2.cu): 1 drops the neighbour exchange, 2 the logit loads
+#endif
+
 namespace isp {
 namespace mas2 {
 
@@ -259,14 +266,33 @@ ISP_DEVINL void strip_forward(const StripCtx& c, bool probe_w, long long* pc_wai
                 if (c.has_prev) pp_seen = ld_volatile_sa(c.prog_sa + 4u * uint32_t(s - 1));
                 if (c.has_next) pn_seen = ld_volatile_sa(c.prog_sa + 4u * uint32_t(s + 1));
             }
+#if ISP_MAS2_ABL & 2
+            const float2 xn2 = xn;
+#else
             const float2 xn2 = lds_f32x2(xa + uint32_t(k) * pitchB);                              // the row of step k + 2
+#endif
             const float s1 = set_ge(q0, q1);                    // mas.py:17 -- ties take j-1
             const float m1 = fmaxf(q0, q1);
             const float s0 = set_ge(left, q0);
             const float m0 = fmaxf(left, q0);
             q1 = xc.y + m1;                                     // mas.py:14 -- one fp32 add per cell
+#if ISP_MAS2_ABL & 1
+            const float l2 = lnext;
+#elif ISP_MAS2_ABL & 4
+            sts_f32(wV + uint32_t(4 * k), q1);
+            const float l2 = lnext;
+#elif ISP_MAS2_ABL & 8
+            const float l2 = lds_f32(rB + uint32_t(4 * k));
+#elif ISP_MAS2_SHFL
+            // the exchange through a shuffle: lane 0 takes the previous strip's boundary value (or -inf), lane 31 publishes its own
+            float l2 = __shfl_up_sync(0xffffffffu, q1, 1);
+            if (c.has_prev) { const float bv = lds_f32(rB + uint32_t(4 * k)); l2 = lane0 ? bv : l2; }
+            else l2 = lane0 ? -CUDART_INF_F : l2;
+            if (c.has_next) sts_f32_if(wV + uint32_t(4 * k), q1, lane31);
+#else
             sts_f32(wV + uint32_t(4 * k), q1);
             const float l2 = lds_f32(rB + uint32_t(4 * k));     // `left` of step k + 2
+#endif
             q0 = xc.x + m0;
             if (k < 8) {
                 acc0 = fmaf(s0, float(1 << (2 * k)), acc0);
@@ -314,6 +340,7 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     else { rank0 = c; rank1 = p.B - 1 - (c - p.nsingle); if (rank1 <= rank0) rank1 = -1; }
     if (rank0 >= p.B) return;
     int b0, b1 = -1, blong;
+    uint32_t key0 = 0, key1 = 0, keyl = 0;              // self-ranking: (frames << 17 | tokens - 1 << 9 | index'), clamped lengths
     if (p.order != nullptr) {
         if (slot == 1 && rank1 < 0) return;
         b0 = p.order[rank0];
@@ -351,12 +378,15 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
         b0 = sel[0];
         if (rank1 >= 0) b1 = sel[1];
         blong = sel[2];
+        key0 = keys[b0]; key1 = keys[b1 >= 0 ? b1 : b0]; keyl = keys[blong];
         __syncthreads();                                // the key scratch becomes the slots' bodies
         if (slot == 1 && rank1 < 0) return;
     }
-    const Geo g0 = make_geo(p.mel_len[b0], p.text_len[b0], p.T1max, p.T2max);
+    // (the keys hold the clamped lengths; the out-of-contract flag needs the originals, which only strip 0's lane 0 re-reads)
+    const bool from_keys = p.order == nullptr;
+    const Geo g0 = from_keys ? make_geo(key0 >> 17, ((key0 >> 9) & 0xffu) + 1, p.T1max, p.T2max) : make_geo(p.mel_len[b0], p.text_len[b0], p.T1max, p.T2max);
     Geo g1 = g0;
-    if (b1 >= 0) g1 = make_geo(p.mel_len[b1], p.text_len[b1], p.T1max, p.T2max);
+    if (b1 >= 0) g1 = from_keys ? make_geo(key1 >> 17, ((key1 >> 9) & 0xffu) + 1, p.T1max, p.T2max) : make_geo(p.mel_len[b1], p.text_len[b1], p.T1max, p.T2max);
     const uint32_t body0 = kZeroPage + 2 * kHdr;
     const uint32_t avail = kSmemTotal - body0;
     int nstg;
@@ -387,7 +417,7 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     // everybody).  So the others are paced: an utterance's loaders spread its chunks over the longest chain's expected sweep.
     float pace = 0.0f;
     if (p.linger && p.pace_cycles_per_step > 0.0f) {
-        const Geo gl = make_geo(p.mel_len[blong], p.text_len[blong], p.T1max, p.T2max);
+        const Geo gl = from_keys ? make_geo(keyl >> 17, ((keyl >> 9) & 0xffu) + 1, p.T1max, p.T2max) : make_geo(p.mel_len[blong], p.text_len[blong], p.T1max, p.T2max);
         const float t_long = float(gl.n + 31 + 51 * (gl.ns - 1)) * p.pace_cycles_per_step;
         pace = t_long / float(g.nch + 3 * (g.ns - 1));
     }
@@ -432,7 +462,10 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     // ---- set-up: barriers, counters, exchange arrays, the zero rows in front of row 0 ----
     if (role == 0) {
         if (lane == 0) {
-            if (s == 0) p.bad[b] = (unsigned char)g.bad;
+            if (s == 0) {
+                const long long n64 = p.mel_len[b], m64 = p.text_len[b];
+                p.bad[b] = (unsigned char)(n64 < 1 || n64 > p.T1max || m64 < 1 || m64 > p.T2max);
+            }
             for (int st = 0; st < nstg; ++st) {
                 mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (full_s - smem_sa)) + st, p.tma ? 1 : 32);
                 mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (empty_s - smem_sa)) + st, 1);
@@ -944,7 +977,7 @@ int mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text
         const double chain_us = (double(T1max) + 31.0 + 50.0 * ((T2max + kStrip - 1) / kStrip - 1)) * 40.0 / (khz * 1e-3) + 5.0;
         const double waves = B > 2 * sm_count ? double(B) / (2.0 * sm_count) : 1.0;
         const double bytes_us = double(B) * T1max * T2max * 4.0 / (0.8 * 6.5e6) / waves;
-        double win_us = 0.85 * (chain_us > bytes_us ? chain_us : bytes_us);
+        double win_us = chain_us > bytes_us ? chain_us : bytes_us;
         if (g2_fill_us > 0) win_us = g2_fill_us;
         p.fill_cycles = float(win_us * khz * 1e-3);
     }
@@ -958,7 +991,7 @@ int mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text
     const int grid = p.nsingle + npair;
     p.linger = grid <= sm_count ? 1 : 0;
     p.together = g2_together;
-    p.pace_cycles_per_step = g2_pace >= 0 ? float(g2_pace) : 44.0f;
+    p.pace_cycles_per_step = g2_pace >= 0 ? float(g2_pace) : 56.0f;      // measured at cfg3: 52 .. 60 is flat, 44 and 70 lose 5 %
     Maps maps;
     memset(&maps, 0, sizeof(maps));
     p.tma = (!no_tma && make_maps2(&maps, logp, sB, sT1, B, T1max, T2max)) ? 1 : 0;
