@@ -86,6 +86,8 @@ constexpr uint32_t kOffTdone = kOffLanded + 16;                   // blocks of 3
 constexpr uint32_t kOffMdone = kOffTdone + 4;                     // blocks of 32 rows the mapper has consumed
 constexpr uint32_t kOffFillDone = kOffMdone + 4;
 constexpr uint32_t kOffSlotDone = kOffFillDone + 4;
+constexpr uint32_t kOffPathDone = kOffSlotDone + 4;               // the path is in shared memory (mapper warp -> transposer warp)
+constexpr uint32_t kOffOnesDone = kOffPathDone + 4;               // the transposer warp has written its half of the ones
 constexpr uint32_t kOffNegInf = 1600;                             // 16 floats of -inf
 
 struct Params {
@@ -189,6 +191,17 @@ struct StripCtx {
     uint32_t v_rd, v_wr;    // exchange array addresses of lanes 1..31 (read) / 0..30 (write); lane 0 / 31 see below
     uint32_t bnd_prev, bnd_mine;
 };
+
+// hard[r][path[r]] = 1 for the rows of one parity of 256-row blocks; eight rows per lane and pass so that the loads overlap
+ISP_DEVINL void write_ones(int16_t* hard_b, uint32_t path_sa, int n, int T2max, int lane, int parity) {
+    for (int r0 = 256 * parity; r0 < n; r0 += 512) {
+        int pj[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int r = r0 + 32 * i + lane; pj[i] = r < n ? lds_s16(path_sa + 2u * r) : 0; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int r = r0 + 32 * i + lane; if (r < n) hard_b[size_t(r) * T2max + pj[i]] = 1; }
+    }
+}
 
 // Out of line on purpose: the sweep's registers stay in registers, and the rare wait costs a call.
 __device__ __noinline__ int3 poll_flags(uint32_t landed_sa, uint32_t prev_sa, uint32_t next_sa, int need_l, int need_p, int need_n) {
@@ -419,7 +432,8 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (p.linger && p.pace_cycles_per_step > 0.0f) {
         const Geo gl = from_keys ? make_geo(keyl >> 17, ((keyl >> 9) & 0xffu) + 1, p.T1max, p.T2max) : make_geo(p.mel_len[blong], p.text_len[blong], p.T1max, p.T2max);
         const float t_long = float(gl.n + 31 + 51 * (gl.ns - 1)) * p.pace_cycles_per_step;
-        pace = t_long / float(g.nch + 3 * (g.ns - 1));
+        // (the chains within a fifth of the longest are the ones being protected: they run free)
+        if (5 * g.n < 4 * gl.n) pace = t_long / float(g.nch + 3 * (g.ns - 1));
     }
     const int n = g.n, m = g.m, nch = g.nch;
     const uint32_t hdr_sa = smem_sa + kZeroPage + uint32_t(slot) * kHdr;
@@ -475,6 +489,8 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
             if (s == 0) {
                 st_volatile_sa(tdone_sa, 0);
                 st_volatile_sa(mdone_sa, 0);
+                st_volatile_sa(hdr_sa + kOffPathDone, 0);
+                st_volatile_sa(hdr_sa + kOffOnesDone, 0);
             }
             fence_mbar_init();
         }
@@ -603,7 +619,8 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
             // utterance that filled its 400 KB block during its own short sweep would, together with the other short ones,
             // saturate HBM for the first third of the launch and starve the long chains that decide when it ends.
             const int pieces = int((size_t(ze - zb) + kZeroPage - 1) / kZeroPage);
-            const float rate = float(pieces) / p.fill_cycles;
+            const float own = 0.8f * 45.0f * float(n + 31 + 51 * (g.ns - 1));           // most of this utterance's own sweep
+            const float rate = float(pieces) / fmaxf(p.fill_cycles, own);
             const long long t0 = clock64();
             int issued = 0;
             uint32_t idle = 0;
@@ -718,6 +735,14 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
             if (lane == 0) st_release_sa(tdone_sa, gb + 1);
         }
         if (probe_w && lane == 0) { p.probe[6] = clock64(); p.probe[7] = tp_p; p.probe[8] = tp_m; }
+        // ... and then the odd half of the path's ones (scattered 2 B stores: one warp's cost ~2 cycles per row in the load /
+        // store unit, two warps' interleave)
+        if (p.hard) {
+            wait_counter_idle(hdr_sa + kOffPathDone, 1, 100);
+            write_ones(p.hard + size_t(b) * p.T1max * p.T2max, body_sa + g.off_path, n, p.T2max, lane, 1);
+            __syncwarp();
+            if (lane == 0) st_release_sa(hdr_sa + kOffOnesDone, 1);
+        }
         return;
     }
 
@@ -779,7 +804,11 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
         const int path0 = j;
         __syncwarp();
         if (probe_w && lane == 0) p.probe[11] = clock64();
-        // ---- expansion: one lane per group walks its 32 rows (mas.py:22-24) ----
+        // ---- expansion: one lane per group walks its 32 rows (mas.py:22-24).  What the walk passes is final, so it leaves as
+        //      it goes: the path's column (to the caller, and to shared memory for the ones below) and the first row of every
+        //      token -- the row the path enters the token's column diagonally.
+        int16_t* path_g = p.path ? p.path + size_t(b) * p.T1max : nullptr;
+        int16_t* hard_b = p.hard ? p.hard + size_t(b) * p.T1max * p.T2max : nullptr;
         for (int gbase = 0; gbase < g.g1; gbase += 32) {
             const int gg = gbase + lane;
             if (gg < g.g1) {
@@ -787,42 +816,25 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
                 const int hi_row = min(32 * gg + 31, n - 1), lo_row = max(32 * gg, 1);
                 for (int i = hi_row; i >= lo_row; --i) {
                     sts_u16(path_sa + 2u * i, jj);
+                    if (path_g) path_g[i] = int16_t(jj);
                     const int L = jj >> 1, u = i + (L & 31);
                     const uint32_t wv = lds_u32(w_sa + (uint32_t(u >> 4) * uint32_t(g.nlp) + uint32_t(L)) * 4u);
-                    jj -= int((wv >> (2 * (u & 15) + (jj & 1))) & 1u);
+                    const uint32_t bit = (wv >> (2 * (u & 15) + (jj & 1))) & 1u;
+                    if (bit) sts_u16(start_sa + 2u * jj, i);
+                    jj -= int(bit);
                 }
-                if (gg == 0) sts_u16(path_sa, jj);
-            }
-        }
-        __syncwarp();
-        if (probe_w && lane == 0) p.probe[12] = clock64();
-        // ---- outputs: the path, its ones in the dense tensor (after the last zero has landed), the first row of every
-        //      token, the durations (alignment.py:275).  Four rows per lane and pass: the loads are independent.
-        wait_counter_idle(filldone_sa, 1, 20);
-        if (probe_w && lane == 0) p.probe[13] = clock64();
-        int16_t* path_g = p.path ? p.path + size_t(b) * p.T1max : nullptr;
-        int16_t* hard_b = p.hard ? p.hard + size_t(b) * p.T1max * p.T2max : nullptr;
-        for (int r0 = 0; r0 < n; r0 += 128) {
-            int pj[4], pv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + 32 * i + lane;
-                pj[i] = r < n ? lds_s16(path_sa + 2u * r) : -1;
-                pv[i] = (r > 0 && r < n) ? lds_s16(path_sa + 2u * (r - 1)) : -1;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + 32 * i + lane;
-                if (r < n) {
-                    if (pj[i] != pv[i]) sts_u16(start_sa + 2u * pj[i], r);
-                    if (path_g) path_g[r] = int16_t(pj[i]);
-                    if (hard_b) hard_b[size_t(r) * p.T2max + pj[i]] = 1;
+                if (gg == 0) {
+                    sts_u16(path_sa, jj);
+                    if (path_g) path_g[0] = int16_t(jj);
+                    sts_u16(start_sa + 2u * jj, 0);
                 }
             }
         }
         if (path_g) for (int r = n + lane; r < p.T1max; r += 32) path_g[r] = -1;
         if (lane == 0) sts_u16(start_sa + 2u * m, n);
         __syncwarp();
+        if (probe_w && lane == 0) p.probe[12] = clock64();
+        // ---- durations (alignment.py:275): the distance between the first rows of neighbouring tokens ----
         if (p.dur) {
             int64_t* d = p.dur + size_t(b) * p.T2max;
             for (int jj = lane; jj < p.T2max; jj += 32) {
@@ -830,6 +842,15 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
                 if (jj < m && jj >= path0) v = int64_t(lds_s16(start_sa + 2u * (jj + 1)) - lds_s16(start_sa + 2u * jj));
                 d[jj] = v;
             }
+        }
+        // ---- the path's ones in the dense tensor, after the last zero has landed; eight rows per lane and pass ----
+        wait_counter_idle(filldone_sa, 1, 20);
+        if (probe_w && lane == 0) p.probe[13] = clock64();
+        if (hard_b) {
+            __syncwarp();
+            if (lane == 0) st_release_sa(hdr_sa + kOffPathDone, 1);       // (the fill has landed: both warps may write)
+            write_ones(hard_b, path_sa, n, p.T2max, lane, 0);
+            wait_counter_idle(hdr_sa + kOffOnesDone, 1, 20);
         }
         if (probe_w && lane == 0) { p.probe[3] = clock64(); p.probe[16] = gtimer(); }
         if (p.trace != nullptr && lane == 0) p.trace[4 * b + 1] = gtimer();
@@ -977,7 +998,8 @@ int mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text
         const double chain_us = (double(T1max) + 31.0 + 50.0 * ((T2max + kStrip - 1) / kStrip - 1)) * 40.0 / (khz * 1e-3) + 5.0;
         const double waves = B > 2 * sm_count ? double(B) / (2.0 * sm_count) : 1.0;
         const double bytes_us = double(B) * T1max * T2max * 4.0 / (0.8 * 6.5e6) / waves;
-        double win_us = chain_us > bytes_us ? chain_us : bytes_us;
+        double win_us = bytes_us;                    // (the kernel stretches it to 80 % of the utterance's own sweep when that is longer)
+        (void)chain_us;
         if (g2_fill_us > 0) win_us = g2_fill_us;
         p.fill_cycles = float(win_us * khz * 1e-3);
     }

@@ -60,7 +60,7 @@ def run(name, impl=0, slots=0, minpair=0, batch=None, dbg=0):
                 f"hops+expansion+outputs {pr[3]-pr[2]} cyc; strip 0 waited {pr[4]} cyc for logits, {pr[5]} for its neighbours; "
                 f"last strip ends +{pr[10]-pr[1]}; transposer ends +{pr[6]-pr[1]} (waited {pr[7]} for strips, {pr[8]} for the mapper); mapper waited {pr[9]}, computed {pr[19]}; "
                 f"plan kernel -> main kernel entry {(pr[17]-pr[18])/1e3:.1f} us, entry -> sweep starts {(pr[15]-pr[17])/1e3:.1f} us, sweep start -> done {(pr[16]-pr[15])/1e3:.1f} us "
-                f"({(pr[3]-pr[0])/max(pr[16]-pr[15],1):.3f} cycles/ns); hops {pr[11]-pr[2]}, expansion {pr[12]-pr[11]}, outputs {pr[13]-pr[12]}, fill wait + ones {pr[3]-pr[13]}")
+                f"({(pr[3]-pr[0])/max(pr[16]-pr[15],1):.3f} cycles/ns); hops {pr[11]-pr[2]}, expansion {pr[12]-pr[11]}, durations + fill wait {pr[13]-pr[12]}, ones {pr[3]-pr[13]}")
     print(msg, flush=True)
     if dbg & 64:
         off = 256 + ((B * 4 + 15) & ~15)
