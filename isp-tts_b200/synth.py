@@ -73,3 +73,43 @@ def encoded_pair(batch: int, t1max: int, t2max: int, dim: int, text_len, mel_len
     q[np.arange(t1max)[None, :] >= np.asarray(mel_len)[:, None]] = 0.0
     k[np.arange(t2max)[None, :] >= np.asarray(text_len)[:, None]] = 0.0
     return q, k
+
+
+# state_dict of the reference Aligner at the recipe's hyper-parameters (recipes/acoustic/core.yaml:150-156 with mel 80,
+# text 384: SURVEY.md A.8): 11 tensors, 1,713,120 parameters
+RECIPE_HP = dict(mel_dim=80, text_dim=384, attention_dim=128, key_kernel_size=5, query_kernel_size=[5, 5],
+                 dropout=0.1, normalization="instance", activation="gelu")
+RECIPE_SHAPES = {
+    "attention.key_proj.0.conv.weight": (768, 384, 5), "attention.key_proj.0.norm.weight": (768,), "attention.key_proj.0.norm.bias": (768,),
+    "attention.key_proj.1.conv.weight": (128, 768, 1),
+    "attention.query_proj.0.conv.weight": (160, 80, 5), "attention.query_proj.0.norm.weight": (160,), "attention.query_proj.0.norm.bias": (160,),
+    "attention.query_proj.1.conv.weight": (80, 160, 5), "attention.query_proj.1.norm.weight": (80,), "attention.query_proj.1.norm.bias": (80,),
+    "attention.query_proj.2.conv.weight": (128, 80, 1),
+}
+
+
+def recipe_state(seed: int):
+    """Seeded weights of the recipe-shape Aligner (numpy): conv weights ~ U(-b, b) with b = 1/sqrt(fan_in) like torch's
+    default init, norm gains around 1, norm biases around 0.  The same seed gives the same weights on every box, so a
+    golden file only has to hold the reference's OUTPUTS for them."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for name, shape in RECIPE_SHAPES.items():
+        if name.endswith("conv.weight"):
+            bound = 1.0 / np.sqrt(shape[1] * shape[2])
+            out[name] = rs.uniform(-bound, bound, size=shape).astype(np.float32)
+        elif name.endswith("norm.weight"):
+            out[name] = (1.0 + 0.1 * rs.standard_normal(shape)).astype(np.float32)
+        else:
+            out[name] = (0.1 * rs.standard_normal(shape)).astype(np.float32)
+    return out
+
+
+def recipe_inputs(seed: int, B: int, T1: int, T2: int, text_len, mel_len):
+    """mel (B, 80, T1) log-mel-like and enc_text (B, 384, T2), zero at padded positions (collator.py:47, transformer.py:206)."""
+    rs = np.random.RandomState(seed)
+    mel = np.clip(rs.standard_normal((B, 80, T1)) * 2 - 5, -11.5, 2.0).astype(np.float32)
+    txt = rs.standard_normal((B, 384, T2)).astype(np.float32)
+    mel *= (np.arange(T1)[None, None] < np.asarray(mel_len)[:, None, None])
+    txt *= (np.arange(T2)[None, None] < np.asarray(text_len)[:, None, None])
+    return mel, txt

@@ -133,11 +133,68 @@ def gen_loglik():
     run("dim128", rec, 3, 260, 48, np.array([48, 31, 40], np.int64), np.array([260, 180, 233], np.int64))
 
 
+def gen_recipe():
+    """The full reference Aligner at the recipe's shape (mel 80, text 384, attention_dim 128, kernels 5: 1.7 M parameters) on
+    seeded weights and inputs (isp_tts_b200.synth.recipe_state / recipe_inputs regenerate both); only outputs are stored."""
+    import torch
+    m = ref_loader.load_alignment()
+    b_mas = ref_loader.load_b_mas()
+    seed, B, T1, T2 = 2024, 2, 300, 60
+    tl, ml = np.array([60, 41], np.int64), np.array([300, 215], np.int64)
+    al = m.Aligner(**synth.RECIPE_HP).eval()
+    assert {k: tuple(v.shape) for k, v in al.state_dict().items()} == synth.RECIPE_SHAPES
+    al.load_state_dict({k: torch.from_numpy(v) for k, v in synth.recipe_state(seed).items()}, strict=True)
+    mel, txt = synth.recipe_inputs(seed + 1, B, T1, T2, tl, ml)
+    with torch.no_grad():
+        soft, logits = al.attention(queries=torch.from_numpy(mel), keys=torch.from_numpy(txt), query_len=torch.from_numpy(ml), key_len=torch.from_numpy(tl))
+    hard = b_mas(logits.numpy().copy(), tl, ml)
+    np.savez_compressed(os.path.join(OUT, "aligner_recipe.npz"), seed=seed, B=B, T1=T1, T2=T2, text_len=tl, mel_len=ml,
+                        attn_logits=logits.numpy(), attn_soft=soft.numpy().astype(np.float16), path=paths_of(hard, ml),
+                        durations=hard.sum(axis=1, dtype=np.int64))
+
+
+def gen_consumers():
+    """The reference's own LengthRegulator and TemporalAverager (temporal_adaptor.py:411-465) on both of their routes: hard
+    durations (the MAS durations of a reference b_mas run) and the recipe's soft route (`alignment` = the Aligner's attn_soft,
+    model.py:154).  Inputs and outputs are stored."""
+    import torch
+    ta = ref_loader.load_temporal_adaptor()
+    b_mas = ref_loader.load_b_mas()
+    B, T1, T2, C = 3, 170, 44, 48
+    tl, ml = synth.lengths(B, T2, T1, True, 301)
+    x_l = synth.noise_logits(B, T1, T2, 302)
+    hard = b_mas(x_l.copy(), tl, ml)
+    dur = torch.from_numpy(hard.sum(axis=1, dtype=np.int64))
+    rs = np.random.RandomState(303)
+    x = torch.from_numpy(rs.standard_normal((B, T2, C)).astype(np.float32))
+    valid = (np.arange(T1)[None, :, None] < ml[:, None, None]) & (np.arange(T2)[None, None, :] < tl[:, None, None])
+    soft = np.where(valid, np.exp(2.0 * x_l), 0.0)
+    soft = (soft / np.maximum(soft.sum(2, keepdims=True), 1e-30)).astype(np.float32)          # rows of valid frames sum to 1
+    soft_t = torch.from_numpy(soft)
+    feat = (rs.rand(B, 2, T1) * 200.0 + 80.0).astype(np.float32)
+    feat[rs.rand(B, 2, T1) < 0.3] = 0.0
+    feat *= (np.arange(T1)[None, None, :] < ml[:, None, None])
+    feat_t = torch.from_numpy(feat)
+    lr, av = ta.LengthRegulator(), ta.TemporalAverager()
+    out_h, dec_h = lr(x, dur, max_len=T1)                                   # temporal_adaptor.py:300 without alignment
+    out_s, dec_s = lr(x, dur, max_len=T1, alignment=soft_t)                 # temporal_adaptor.py:300 on the soft route
+    fdur = dur.float() + torch.from_numpy(rs.uniform(-0.45, 0.45, size=tuple(dur.shape)).astype(np.float32)) * (dur > 0)
+    out_f, dec_f = lr(x, fdur)                                              # :325 shape of call, predicted (float) durations
+    avg_h = av(feat_t, dur)                                                 # :447-465
+    avg_s = av(feat_t, dur, soft_t)                                         # :446-449
+    np.savez_compressed(os.path.join(OUT, "consumers.npz"), text_len=tl, mel_len=ml, durations=dur.numpy(), x=x.numpy(),
+                        attn_soft=soft, path=paths_of(hard, ml), feat=feat, float_durations=fdur.numpy(),
+                        lr_hard=out_h.numpy(), lr_hard_len=dec_h.numpy(), lr_soft=out_s.numpy(), lr_soft_len=dec_s.numpy(),
+                        lr_float=out_f.numpy(), lr_float_len=dec_f.numpy(), avg_hard=avg_h.numpy(), avg_soft=avg_s.numpy())
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         sys.exit("reference not found at " + ref_loader.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
-    gen_mas()
-    gen_loglik()
+    only = [a[7:] for a in sys.argv if a.startswith("--only=")]
+    for name, fn in (("mas", gen_mas), ("loglik", gen_loglik), ("recipe", gen_recipe), ("consumers", gen_consumers)):
+        if not only or name in only:
+            fn()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote", sorted(os.listdir(OUT)), f"{total/1e6:.2f} MB")

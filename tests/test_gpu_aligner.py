@@ -63,3 +63,40 @@ def test_autocast_uses_bf16_and_grads_flow(cuda_device):
     grads = [p.grad for p in al.parameters()]
     assert all(gr is not None and torch.isfinite(gr).all() for gr in grads)
     assert sum(float(gr.abs().sum()) for gr in grads) > 0
+
+
+def test_recipe_shape_matches_reference(cuda_device):
+    """The Aligner at the recipe's hyper-parameters (recipes/acoustic/core.yaml:150-156: mel 80, text 384, attention_dim 128,
+    kernels 5, gelu, instance norm; 1.7 M parameters) against the reference's outputs for the same seeded weights and inputs
+    (oracle/gen_golden.py::gen_recipe froze only the outputs; isp_tts_b200.synth regenerates weights and inputs)."""
+    from isp_tts_b200 import synth
+    g = golden("aligner_recipe.npz")
+    seed, B, T1, T2 = int(g["seed"]), int(g["B"]), int(g["T1"]), int(g["T2"])
+    tl, ml = g["text_len"], g["mel_len"]
+    al = Aligner(**synth.RECIPE_HP).eval()
+    assert {k: tuple(v.shape) for k, v in al.state_dict().items()} == synth.RECIPE_SHAPES        # same keys, same shapes
+    assert sum(v.numel() for v in al.state_dict().values()) == 1_713_120
+    al.load_state_dict({k: torch.from_numpy(v) for k, v in synth.recipe_state(seed).items()}, strict=True)
+    al = al.to(cuda_device)
+    mel, txt = synth.recipe_inputs(seed + 1, B, T1, T2, tl, ml)
+    with torch.no_grad():
+        out = al(torch.from_numpy(mel).to(cuda_device), torch.from_numpy(txt).to(cuda_device),
+                 torch.from_numpy(ml).to(cuda_device), torch.from_numpy(tl).to(cuda_device))
+    soft, logits, hard, dur = (t.cpu().numpy() for t in out)
+    ref = g["attn_logits"]
+    valid = (np.arange(T1)[None, :, None] < ml[:, None, None]) & (np.arange(T2)[None, None, :] < tl[:, None, None])
+    # cells within 2 % of the prior's 1e-4 threshold may fall on either side of it (a jump of ~4.6 in the logit): leave out
+    # rows' cells whose reference value and ours differ by that jump, but bound how many there are
+    err = np.abs(logits - ref)
+    tol = 1e-3 * np.abs(ref) + 2e-3            # TF32 products through two conv stacks
+    bad = (err > tol) & valid
+    assert bad.sum() <= max(4, valid.sum() // 2000), (int(bad.sum()), float(err[valid].max()))
+    assert np.abs(soft - g["attn_soft"].astype(np.float32))[valid].max() < 5e-3
+    assert soft[~valid].sum() == 0.0
+    rh, rd = omas.b_mas_with_durations(logits, tl, ml)                       # bit-exact given our logits
+    assert np.array_equal(hard, rh) and np.array_equal(dur, rd)
+    path = hard.argmax(axis=2)
+    frames = int(ml.sum())
+    moved = sum(int((path[b, :ml[b]] != g["path"][b, :ml[b]]).sum()) for b in range(B))
+    assert moved <= max(2, frames // 100), f"{moved} of {frames} frames moved against the reference's path"
+    assert np.array_equal(dur.sum(1), ml)

@@ -233,3 +233,38 @@ def test_stage_operands_ragged_upload(cuda_device, dtype):
     assert torch.equal(s1, s2) and torch.equal(l1, l2)
     with pytest.raises(ValueError):
         stage_operands(clean_q, clean_k, tlt, mlt)            # not pinned
+
+
+def _full_size_against_oracle(dev, name, dtype, chunk):
+    """The kernel on a BASELINE.json workload at full size, compared utterance chunk by utterance chunk with the numpy
+    oracle (oracle/loglik.py) so that the CPU side runs in seconds."""
+    w = synth.WORKLOADS[name]
+    tl, ml = synth.workload_lengths(w)
+    q, k = synth.encoded_pair(w.batch, w.t1max, w.t2max, w.dim, tl, ml, w.seed + 1)
+    if dtype == "bf16":                # compare at the operands' precision (see test_against_oracle)
+        q = torch.from_numpy(q).to(torch.bfloat16).float().numpy()
+        k = torch.from_numpy(k).to(torch.bfloat16).float().numpy()
+    soft, logits = run(q, k, tl, ml, dev, dtype)
+    tol = TOL["fp32"] if dtype == "fp32" else dict(rel=1e-3, abs=1e-4, soft=1e-3)
+    worst = 0.0
+    for b0 in range(0, w.batch, chunk):
+        sl = slice(b0, min(b0 + chunk, w.batch))
+        rs, rl, parts = oll.loglik(q[sl], k[sl], tl[sl], ml[sl], return_parts=True)
+        amb = oll.threshold_ambiguous(parts["prior_raw"])
+        e, _ = compare(soft[sl], logits[sl], rs, rl, amb, tol, f"{name}/{dtype} utterances {b0}..")
+        worst = max(worst, e)
+    # size-independent structure: soft mass only inside each window, valid rows sum to one
+    rows = np.arange(w.t1max)[None, :] < ml[:, None]
+    assert np.allclose(soft.sum(2)[rows], 1.0, atol=2e-4)
+    assert soft[~rows].sum() == 0.0
+    return worst
+
+
+def test_full_size_cfg3_bf16_against_oracle(cuda_device):
+    """BASELINE.json configs[2], the bench workload itself: batch 256 ragged x 1000 x 200, bf16 operands."""
+    _full_size_against_oracle(cuda_device, "cfg3", "bf16", 16)
+
+
+def test_full_size_cfg4_against_oracle(cuda_device):
+    """BASELINE.json configs[3]: 512 tokens x 4096 frames, batch 16 (both TMEM accumulator chunks, 32 frame tiles per utterance)."""
+    _full_size_against_oracle(cuda_device, "cfg4", "bf16", 1)

@@ -328,3 +328,52 @@ def test_path_only_without_dense_output(cuda_device, T2):
         assert torch.equal(hard[b, :ml[b]].argmax(dim=1).to(torch.int16), path[b, :ml[b]])
     with pytest.raises(ValueError):
         mas_forward(xt, torch.from_numpy(tl), torch.from_numpy(ml), dense=False)
+
+
+def _realistic_logits(dev, name, batch=None):
+    """attn_logits as the hot path produces them (values in about [-20, -5], 41 % of the valid cells on the
+    log(1e-6) plateau of the prior): the log-likelihood kernel's own output on the workload's synthetic encodings."""
+    from isp_tts_b200.alignment import loglik_forward
+    w = synth.WORKLOADS[name]
+    tl, ml = synth.workload_lengths(w, batch)
+    B = len(tl)
+    q, k = synth.encoded_pair(B, w.t1max, w.t2max, w.dim, tl, ml, w.seed + 1)
+    soft, logits = loglik_forward(torch.from_numpy(q).to(dev).to(torch.bfloat16), torch.from_numpy(k).to(dev).to(torch.bfloat16),
+                                  torch.from_numpy(tl).to(dev), torch.from_numpy(ml).to(dev))
+    return logits, tl, ml
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4"])
+def test_realistic_logits_against_oracle(cuda_device, name):
+    """MAS on the SAME fp32 tensor for both sides: the kernel's own attn_logits into mas_forward and into the oracle."""
+    logits, tl, ml = _realistic_logits(cuda_device, name)
+    hard, dur = mas_forward(logits, torch.from_numpy(tl), torch.from_numpy(ml))
+    torch.cuda.synchronize()
+    x = logits.cpu().numpy()
+    valid = (np.arange(x.shape[1])[None, :, None] < ml[:, None, None]) & (np.arange(x.shape[2])[None, None, :] < tl[:, None, None])
+    plateau = np.isclose(x, np.log(np.float32(1e-6)), atol=3.0) & valid            # prior floor + (S - lse) within a few units
+    assert x[valid].min() > -60 and x[valid].max() < 0 and plateau.sum() > 0.2 * valid.sum()
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard.cpu().numpy(), dur.cpu().numpy(), rh, rd, f"{name} realistic logits")
+    assert np.array_equal(dur.cpu().numpy().sum(1), ml)
+
+
+@pytest.mark.parametrize("mode", ["auto", "two_slots", "v1"])
+def test_all_plateau_adversarial(cuda_device, mode):
+    """Every valid cell on the prior's floor (one constant): every comparison of the DP is a tie, so the tie rule alone
+    decides the path (surplus frames go to the FIRST token); then the same with one better column."""
+    set_mode(mode)
+    B, T1, T2 = 7, 333, 150
+    tl, ml = synth.lengths(B, T2, T1, True, 71)
+    tl[1], ml[1] = 150, 149                                      # more tokens than frames: the pure diagonal
+    x = np.full((B, T1, T2), np.log(np.float32(1e-6)), dtype=np.float32)
+    hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, "all plateau")
+    for b in range(B):
+        if ml[b] >= tl[b]:
+            assert dur[b, 0] == ml[b] - tl[b] + 1 and np.all(dur[b, 1:tl[b]] == 1)
+    x[:, :, 40] += np.float32(0.5)                               # a ridge in one column
+    hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, "plateau with a ridge")
