@@ -106,10 +106,27 @@ int    isp_length_regulate(const void* x, const int16_t* path, void* out, int dt
                            int B, int T1max, int T2max, int C, void* stream);
 int    isp_length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
                                     int B, int T1max, int T2max, int C, void* stream);
+/* The path (token index per frame, -1 past the utterance's total) from rounded durations, for callers without a MAS path:
+ * the reference's inference route builds a (T1 x T2) 0/1 matrix from the cumulated durations instead
+ * (tts/models/acoustic/modules/temporal_adaptor.py:424-431).  reps (B, T2max) int64 = (durations + 0.5) truncated;
+ * path (B, T1max) int16. */
+int    isp_path_from_durations(const int64_t* reps, int16_t* path, int B, int T1max, int T2max, void* stream);
 /* Per-token average of frame-level features (tts/models/acoustic/modules/temporal_adaptor.py:439-465, `durations` branch):
  * out[b, c, j] = sum of x[b, c, t] over the token's frames / count of non-zero x among them (0 if none).
  * x (B, C, T1max) fp32, durations (B, T2max) int64 (the MAS durations), out (B, C, T2max) fp32, all contiguous. */
 int    isp_temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, void* stream);
+/* The same average on the recipe's soft route (temporal_adaptor.py:446-449, `alignment` = the Aligner's attn_soft,
+ * tts/models/acoustic/model.py:154):  out[b, c, j] = sum_t x[b, c, t] * a[b, t, j] / (sum_t a[b, t, j] + 1e-5).
+ * One streaming pass over attn_soft in fp32 (no tensor-core rounding), deterministic two-stage sum.
+ * x (B, C, T1max) fp32, C <= 4; attn_soft (B, T1max, T2max) fp32, T2max % 4 == 0, 16 B aligned; row_len optional DEVICE
+ * int64 (B,): rows >= row_len[b] are known to be zero and are not read; out (B, C, T2max); colsum optional (B, T2max), the
+ * denominators without the 1e-5 (the backward needs them); ws: isp_soft_average_workspace_bytes(...) bytes, 16 B aligned.
+ * Backward: g_soft[b, t, j] = sum_c g[b, c, j] / (colsum[b, j] + 1e-5) * (x[b, c, t] - out[b, c, j]). */
+size_t isp_soft_average_workspace_bytes(int B, int C, int T1max, int T2max);
+int    isp_soft_average(const float* x, const float* attn_soft, const int64_t* row_len, float* out, float* colsum,
+                        int B, int C, int T1max, int T2max, void* ws, size_t ws_bytes, void* stream);
+int    isp_soft_average_backward(const float* g, const float* x, const float* out, const float* colsum, float* g_soft,
+                                 int B, int C, int T1max, int T2max, void* stream);
 /* Forward-sum (CTC) alignment loss, tts/models/acoustic/loss.py:41-79 (AttentionCTCLoss.forward): blank column of value
  * blank_logprob in front of attn_logits (:67), log_softmax over the T2max + 1 columns (:69), CTC with targets
  * 1 .. text_len[b] over mel_len[b] frames (:73-78).  isp_ctc_forward writes nll[b] (fp32, natural log; +inf when no
@@ -175,6 +192,40 @@ int    isp_loglik_forward(const void* Q, const void* K, int dtype,
 int    isp_loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
                               int B, int T1max, int T2max, float scale, int attention_prior,
                               void* dS, int ds_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched, ragged GEMM on the tensor cores (tcgen05.mma, TMA operands, accumulator in TMEM):
+ *     C[b] = act(alpha * A[b] . B[b]),   A[b] (M x K), B[b] (K x N), C[b] (M x N, row-major, ldc), fp32 accumulate.
+ * The contractions next to the hot path are all instances of it:
+ *   scores / dQ / dK of the log-likelihood's backward   tts/models/acoustic/modules/alignment.py:189 (differentiated)
+ *   the soft-alignment length regulator and its grads   tts/models/acoustic/modules/temporal_adaptor.py:417-419
+ *   the Conv1d layers of the projection stacks          alignment.py:40-83,118-154 (implicit GEMM over `taps` row shifts)
+ * Operand storage:  a_mn_major = 0: A[b][m][k] at a + b*a_batch + m*lda + k   (the contraction index contiguous)
+ *                   a_mn_major = 1: A[b][m][k] at a + b*a_batch + k*lda + m   (the row index contiguous: a transposed view)
+ *                   b_mn_major = 0: B[b][k][n] at b + b*b_batch + n*ldb + k;  b_mn_major = 1: at b + b*b_batch + k*ldb + n
+ * a_batch / b_batch = 0 shares the operand between batch entries.  dtype_ab: ISP_DTYPE_BF16, or ISP_DTYPE_F32 (fp32 in
+ * memory, TF32 products).  dtype_c: ISP_DTYPE_F32 or ISP_DTYPE_BF16.  Every pointer and every stride must be a multiple
+ * of 16 B.
+ * Ragged batches (all optional, DEVICE int64 (batch,)): rows >= m_len[b] and columns >= n_len[b] of C[b] are written as
+ * zeros (unless skip_padding, which leaves whole padded tiles untouched); the contraction stops at k_len[b] rounded up to
+ * 128 B of K -- the caller guarantees that one operand is zero from k_len[b] on.
+ * Convolution: taps > 1 makes it  C[b][m][n] = act(alpha * sum_t sum_k A[b][m + t + tap_shift][k] * B_t[k][n])  with
+ * B_t at b + t*b_tap_stride (b_batch must be 0, A K-major); rows outside [0, M) read as zeros.
+ * act: 0 none, 1 ReLU, 2 GELU (erf).  col_stats (optional, fp32 (batch, 4*ceil(M/128), N, 2)): per 32-row slab the
+ * column sums of C and of C^2 after masking (the masked-instance-norm statistics, tts/modules/normalization.py:160-208);
+ * slabs of padded tiles are not written (pre-zero the buffer).
+ * bn: tile width 64 / 128 / 256, 0 = chosen from N. */
+typedef struct isp_gemm_desc {
+    const void* a; const void* b; void* c;
+    const int64_t* m_len; const int64_t* n_len; const int64_t* k_len;
+    float* col_stats;
+    int64_t lda, ldb, ldc, a_batch, b_batch, c_batch, b_tap_stride;
+    int32_t batch, M, N, K;
+    int32_t dtype_ab, dtype_c, a_mn_major, b_mn_major;
+    int32_t taps, tap_shift, act, bn, skip_padding;
+    float alpha;
+} isp_gemm_desc;
+int    isp_gemm_batched(const isp_gemm_desc* desc, void* stream);
 
 /* Tuning knobs for benchmarks/tests (process-wide, not part of the drop-in contract).
  *   "mas.ring_rows"      rows of logits kept in flight per strip of 128 tokens, 0 = heuristic

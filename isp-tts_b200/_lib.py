@@ -16,11 +16,24 @@ ISP_DTYPE_BF16 = 1
 
 EXPORTS = [
     "isp_version", "isp_last_error", "isp_device_check",
-    "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_temporal_average", "isp_ctc_workspace_bytes", "isp_ctc_forward", "isp_ctc_backward", "isp_mas_status",
-    "isp_stage_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_set_option",
+    "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_path_from_durations", "isp_temporal_average", "isp_ctc_workspace_bytes", "isp_ctc_forward", "isp_ctc_backward", "isp_mas_status",
+    "isp_stage_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_gemm_batched", "isp_soft_average_workspace_bytes", "isp_soft_average", "isp_soft_average_backward", "isp_set_option",
 ]
 
 _lib = None
+
+
+class GemmDesc(ctypes.Structure):
+    """isp_gemm_desc of include/isp_tts_b200.h."""
+    _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("c", ctypes.c_void_p),
+                ("m_len", ctypes.c_void_p), ("n_len", ctypes.c_void_p), ("k_len", ctypes.c_void_p),
+                ("col_stats", ctypes.c_void_p),
+                ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64), ("ldc", ctypes.c_int64),
+                ("a_batch", ctypes.c_int64), ("b_batch", ctypes.c_int64), ("c_batch", ctypes.c_int64), ("b_tap_stride", ctypes.c_int64),
+                ("batch", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("dtype_ab", ctypes.c_int32), ("dtype_c", ctypes.c_int32), ("a_mn_major", ctypes.c_int32), ("b_mn_major", ctypes.c_int32),
+                ("taps", ctypes.c_int32), ("tap_shift", ctypes.c_int32), ("act", ctypes.c_int32), ("bn", ctypes.c_int32),
+                ("skip_padding", ctypes.c_int32), ("alpha", ctypes.c_float)]
 
 
 class IspError(RuntimeError):
@@ -53,6 +66,8 @@ def load():
     lib.isp_length_regulate.restype = c_int
     lib.isp_length_regulate_backward.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp]
     lib.isp_length_regulate_backward.restype = c_int
+    lib.isp_path_from_durations.argtypes = [vp, vp, c_int, c_int, c_int, vp]
+    lib.isp_path_from_durations.restype = c_int
     lib.isp_temporal_average.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, vp]
     lib.isp_temporal_average.restype = c_int
     lib.isp_ctc_workspace_bytes.argtypes = [c_int, c_int, c_int]
@@ -71,6 +86,14 @@ def load():
     lib.isp_loglik_forward.restype = c_int
     lib.isp_loglik_backward_ds.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, f32, c_int, vp, c_int, vp]
     lib.isp_loglik_backward_ds.restype = c_int
+    lib.isp_soft_average_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.isp_soft_average_workspace_bytes.restype = c_sz
+    lib.isp_soft_average.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, c_sz, vp]
+    lib.isp_soft_average.restype = c_int
+    lib.isp_soft_average_backward.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp]
+    lib.isp_soft_average_backward.restype = c_int
+    lib.isp_gemm_batched.argtypes = [ctypes.POINTER(GemmDesc), vp]
+    lib.isp_gemm_batched.restype = c_int
     lib.isp_set_option.argtypes = [ctypes.c_char_p, c_int]
     lib.isp_set_option.restype = c_int
     _lib = lib

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["length_regulate", "LengthRegulator", "temporal_average", "TemporalAverager"]
+__all__ = ["length_regulate", "path_from_durations", "LengthRegulator", "temporal_average", "TemporalAverager"]
 
 
 class _LengthRegulate(torch.autograd.Function):
@@ -43,7 +43,7 @@ class _LengthRegulate(torch.autograd.Function):
         lib = _lib.load()
         dev = g.device
         g32 = g.float().contiguous()
-        dur = durations.to(torch.int64).contiguous()
+        dur = _round_durations(durations)              # the same rounding as the forward (temporal_adaptor.py:423)
         starts = (torch.cumsum(dur, dim=1) - dur).contiguous()
         gx = torch.empty((B, T2, C), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -51,6 +51,28 @@ class _LengthRegulate(torch.autograd.Function):
                                                   torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "isp_length_regulate_backward")
         return gx.to(ctx.dtype), None, None
+
+
+def _round_durations(durations: torch.Tensor) -> torch.Tensor:
+    """reps = (durations.float() + 0.5).long(), temporal_adaptor.py:423 (integer durations pass through unchanged)."""
+    if durations.dtype in (torch.int64, torch.int32, torch.int16):
+        return durations.to(torch.int64).contiguous()
+    return (durations.float() + 0.5).long().contiguous()
+
+
+def path_from_durations(durations: torch.Tensor, t1max: int) -> torch.Tensor:
+    """(B, t1max) int16 token index per frame from durations (rounded like the reference does), -1 past each utterance's
+    total: what mas_forward(..., return_path=True) returns, for callers that only hold durations (inference)."""
+    dev = durations.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    reps = _round_durations(durations)
+    B, T2 = reps.shape
+    path = torch.empty((B, int(t1max)), dtype=torch.int16, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.isp_path_from_durations(reps.data_ptr(), path.data_ptr(), B, int(t1max), T2, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "isp_path_from_durations")
+    return path
 
 
 def length_regulate(x: torch.Tensor, path: torch.Tensor, durations: torch.Tensor) -> torch.Tensor:
@@ -62,14 +84,26 @@ def length_regulate(x: torch.Tensor, path: torch.Tensor, durations: torch.Tensor
 
 
 class LengthRegulator(torch.nn.Module):
-    """Same call as the reference module when it is fed hard durations (temporal_adaptor.py:411-436), plus `path`:
-    forward(x, durations, max_len=None, path=...) -> (out, dec_lens)."""
+    """The reference module's call, argument for argument (temporal_adaptor.py:411-436):
+    forward(x, durations, max_len=None, alignment=None) -> (out, dec_lens), plus the optional `path`.
 
-    def forward(self, x, durations, max_len=None, path=None):
-        if path is None:
-            raise _lib.IspError("LengthRegulator needs the path from mas_forward(..., return_path=True); there is no CPU / dense fallback")
-        dec_lens = (durations.float() + 0.5).long().sum(dim=1)
-        out = length_regulate(x, path, durations)
+    * `alignment` given (the recipe's soft_duration route, temporal_adaptor.py:300,325): out = alignment @ x, the
+      (B, T1, T2) x (B, T2, C) contraction of :418-419, in the sm_100a batched GEMM (soft_expand).
+    * else hard durations: a gather along the path.  `path` is what mas_forward(..., return_path=True) returned; without it
+      (inference with predicted durations) it is rebuilt on the device from the rounded durations."""
+
+    def forward(self, x, durations, max_len=None, alignment=None, path=None):
+        if alignment is not None:
+            from .soft import soft_expand
+            dec_lens = (durations.sum(dim=1) + 0.5).long()
+            out = soft_expand(alignment, x)
+        else:
+            reps = _round_durations(durations)
+            dec_lens = reps.sum(dim=1)
+            if path is None:
+                t1 = int(dec_lens.max())                       # a host sync, as in the reference (:429)
+                path = path_from_durations(reps, t1)
+            out = length_regulate(x, path, durations)
         if max_len is not None:
             out = out[:, :max_len]
             dec_lens = torch.clamp_max(dec_lens, max_len)
@@ -97,10 +131,12 @@ def temporal_average(x: torch.Tensor, durations: torch.Tensor) -> torch.Tensor:
 
 
 class TemporalAverager(torch.nn.Module):
-    """Same call as the reference module (temporal_adaptor.py:439-465).  With hard durations the average is one kernel;
-    with a soft `alignment` it is the reference's own matmul (a plain library GEMM, not part of the hot path)."""
+    """Same call as the reference module (temporal_adaptor.py:439-465).  With hard durations the average is one kernel
+    (temporal_average); with a soft `alignment` (the recipe's soft_duration route) it is soft_average: x @ alignment divided
+    by the alignment's column sums + 1e-5 (:446-449) in one pass over the alignment."""
 
     def forward(self, x, durations, alignment=None):
         if alignment is not None:
-            return x @ alignment / (alignment.sum(dim=1, keepdim=True) + 1e-5)
+            from .soft import soft_average
+            return soft_average(x, alignment)
         return temporal_average(x, durations)

@@ -114,6 +114,10 @@ int isp_length_regulate_backward(const float* g, const int64_t* durations, const
     return isp::length_regulate_backward(g, durations, starts, gx, B, T1max, T2max, C, static_cast<cudaStream_t>(stream));
 }
 
+int isp_path_from_durations(const int64_t* reps, int16_t* path, int B, int T1max, int T2max, void* stream) {
+    return isp::path_from_durations(reps, path, B, T1max, T2max, static_cast<cudaStream_t>(stream));
+}
+
 int isp_temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, void* stream) {
     return isp::temporal_average(x, durations, out, B, C, T1max, T2max, static_cast<cudaStream_t>(stream));
 }
@@ -136,6 +140,20 @@ int isp_stage_operands(const void* q_host, const void* k_host, int dtype, const 
                        int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* stream) {
     return isp::stage_operands(q_host, k_host, dtype, text_len, mel_len, B, T1max, T2max, D, q_dev, k_dev, static_cast<cudaStream_t>(stream));
 }
+
+size_t isp_soft_average_workspace_bytes(int B, int C, int T1max, int T2max) { return isp::soft_average_workspace_bytes(B, C, T1max, T2max); }
+
+int isp_soft_average(const float* x, const float* attn_soft, const int64_t* row_len, float* out, float* colsum, int B, int C,
+                     int T1max, int T2max, void* ws, size_t ws_bytes, void* stream) {
+    return isp::soft_average(x, attn_soft, row_len, out, colsum, B, C, T1max, T2max, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int isp_soft_average_backward(const float* g, const float* x, const float* out, const float* colsum, float* g_soft, int B, int C,
+                              int T1max, int T2max, void* stream) {
+    return isp::soft_average_backward(g, x, out, colsum, g_soft, B, C, T1max, T2max, static_cast<cudaStream_t>(stream));
+}
+
+int isp_gemm_batched(const isp_gemm_desc* desc, void* stream) { return isp::gemm_batched(desc, static_cast<cudaStream_t>(stream)); }
 
 int isp_set_option(const char* key, int value) {
     if (!key) return ISP_ERR_INVALID;

@@ -1,0 +1,394 @@
+// Batched, ragged GEMM for sm_100a: C[b] = act(alpha * A[b] . B[b]) with TMA-fed tcgen05.mma and the accumulator in TMEM.
+//
+// One kernel behind every dense contraction next to the Aligner's hot path:
+//   f-1  scores S = Q.K^T, dQ = dS.K, dK = dS^T.Q      (tts/models/acoustic/modules/alignment.py:189 differentiated)
+//   f-3  LengthRegulator on the soft route, out = attn_soft @ x and its two gradients
+//        (tts/models/acoustic/modules/temporal_adaptor.py:417-419)
+//   f-2  the Conv1d layers of the projection stacks as implicit GEMMs over `taps` shifted row windows of a
+//        channels-last activation, GELU / ReLU and the masked-instance-norm column sums in the epilogue
+//        (alignment.py:40-83,118-154; tts/modules/normalization.py:160-208)
+//
+// Layout of one CTA (192 threads, one 128 x BN tile of one batch entry):
+//   warp 0      producer: one lane issues the TMA loads of a stage (A: 128 rows x 128 B, B: BN rows x 128 B, both with
+//               the 128 B swizzle) into a ring of `stages` buffers guarded by full / empty mbarriers.
+//   warp 1      owns TMEM (BN fp32 columns x 128 lanes); one lane issues 4 tcgen05.mma per stage (kind::f16 for bf16
+//               operands, kind::tf32 for fp32 operands) and releases the stage with tcgen05.commit.
+//   warps 2-5   epilogue: tcgen05.ld of 32 accumulator columns per step, alpha / activation / ragged masks in
+//               registers, the 32 x 128 B chunk staged in shared memory (swizzled, conflict-free) and written with one
+//               TMA store per chunk (coalesced, clipped at the tensor's bounds by the hardware).
+// Operands may be K-major (the contraction index contiguous) or MN-major (the row / column index contiguous): the
+// second is a different TMA box and shared-memory descriptor (leading byte offset between 128 B-wide chunks), so
+// transposed uses of a tensor (dS^T, x as (T2, C)) need no copy.  Ragged batches: tiles past m_len[b] / n_len[b] are
+// filled with zeros without touching TMEM, rows and columns past the lengths inside a tile are masked, and the
+// contraction stops at k_len[b].
+// With BN <= 128 two CTAs share an SM (<= 256 TMEM columns and <= 96 KB each), so one tile's epilogue runs under the
+// other's loads and MMAs; BN = 256 uses four stages and one CTA per SM (the compute-bound convolution).
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "isp_internal.h"
+#include "isp_tc05.cuh"
+
+namespace isp {
+
+namespace {
+
+constexpr int kGM = 128;                 // tile rows = UMMA M
+constexpr int kGThreads = 192;
+constexpr int kStageA = kGM * 128;       // bytes of A per stage
+constexpr int kMaxStages = 6;
+
+struct GemmParams {
+    const int64_t* m_len;
+    const int64_t* n_len;
+    const int64_t* k_len;
+    unsigned char* c;
+    float* col_stats;
+    long long ldc, c_batch;              // elements
+    int batch, M, N, K;
+    int BN, stages, kb, kblocks;
+    int taps, tap_shift;
+    int a_mn, b_mn, a_shared, b_mode;    // b_mode: third TMA coordinate of B = 0: batch, 1: zero, 2: tap
+    int c_bf16, act, fill_padding;
+    int parts;                           // row partitions of the column statistics: m_tiles * 4
+    float alpha;
+    uint32_t idesc;
+};
+
+ISP_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+ISP_DEVINL uint32_t pack_bf16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(kGThreads)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * p.BN, m0 = blockIdx.y * kGM, b = blockIdx.z;
+
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t stage_bytes = kStageA + uint32_t(p.BN) * 128u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + size_t(p.stages) * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kMaxStages;
+    uint64_t* acc_full = bars + 2 * kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+
+    auto clampi = [](long long v, int hi) { return int(v < 0 ? 0 : (v > hi ? hi : v)); };
+    const int m_valid = p.m_len ? clampi(p.m_len[b], p.M) : p.M;
+    const int n_valid = p.n_len ? clampi(p.n_len[b], p.N) : p.N;
+    const int k_valid = p.k_len ? clampi(p.k_len[b], p.K) : p.K;
+    const int kblocks = (k_valid + p.kb - 1) / p.kb;
+    const int kiters = p.taps * kblocks;
+
+    if (m0 >= m_valid || n0 >= n_valid || kiters == 0) {
+        // nothing of this tile is inside the batch entry's own extent: zeros, straight from registers
+        if (!p.fill_padding) return;
+        const int esz = p.c_bf16 ? 2 : 4;
+        const int rows = min(kGM, p.M - m0);
+        const int row_bytes = min(p.BN, p.N - n0) * esz;
+        const int vecs = row_bytes >> 4;
+        unsigned char* cb = p.c + (size_t(b) * p.c_batch + size_t(m0) * p.ldc + n0) * esz;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int idx = threadIdx.x; idx < rows * vecs; idx += kGThreads) {
+            const int r = idx / vecs, v = idx - r * vecs;
+            st_cs_v4(cb + size_t(r) * p.ldc * esz + size_t(v) * 16, z);
+        }
+        const int tail = row_bytes - (vecs << 4);          // N * esz not a multiple of 16 B
+        if (tail) {
+            for (int idx = threadIdx.x; idx < rows * (tail >> 1); idx += kGThreads) {
+                const int r = idx / (tail >> 1), v = idx - r * (tail >> 1);
+                *reinterpret_cast<uint16_t*>(cb + size_t(r) * p.ldc * esz + (vecs << 4) + v * 2) = 0;
+            }
+        }
+        return;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+        tc::prefetch_tmap(&tmap_c);
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, uint32_t(p.BN < 32 ? 32 : p.BN));
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int me = TF32 ? 32 : 64;                 // M/N indices per 128 B row of an MN-major operand
+    const uint32_t lbo = uint32_t(p.kb) * 128u;    // bytes between two such chunks (one TMA box each)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = uint32_t(it / p.stages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                const int tap = it / kblocks, kbi = it - tap * kblocks;
+                unsigned char* sa = base + size_t(s) * stage_bytes;
+                unsigned char* sb = sa + kStageA;
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                const int ab = p.a_shared ? 0 : b;
+                if (!p.a_mn) {
+                    tc::tma_load_3d(sa, &tmap_a, kbi * p.kb, m0 + tap + p.tap_shift, ab, &full[s]);
+                } else {
+                    for (int c = 0; c < kGM / me; ++c) tc::tma_load_3d(sa + c * lbo, &tmap_a, m0 + c * me, kbi * p.kb, ab, &full[s]);
+                }
+                const int third = p.b_mode == 0 ? b : (p.b_mode == 1 ? 0 : tap);
+                if (!p.b_mn) {
+                    tc::tma_load_3d(sb, &tmap_b, kbi * p.kb, n0, third, &full[s]);
+                } else {
+                    for (int c = 0; c < p.BN / me; ++c) tc::tma_load_3d(sb + c * lbo, &tmap_b, n0 + c * me, kbi * p.kb, third, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t kstep_mn = (TF32 ? 8u : 16u) * 128u;      // bytes per MMA k-step of an MN-major operand
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = uint32_t(it / p.stages) & 1u;
+                mbar_wait(&full[s], ph);
+                tc::fence_after();
+                const uint32_t sa = smem_u32(base + size_t(s) * stage_bytes);
+                const uint32_t sb = sa + kStageA;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // MN-major: 16-bit operands use the plain 128 B swizzle (8 k-rows per atom); TF32 the 32 B-atom form (4 k-rows)
+                    const uint64_t ad = p.a_mn ? tc::smem_desc_sw128(sa + k * kstep_mn, lbo, TF32 ? 512 : 1024, TF32 ? 1 : 2)
+                                               : tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t bd = p.b_mn ? tc::smem_desc_sw128(sb + k * kstep_mn, lbo, TF32 ? 512 : 1024, TF32 ? 1 : 2)
+                                               : tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+                    tc::umma<TF32>(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                tc::umma_commit(&empty[s]);
+            }
+            tc::umma_commit(acc_full);
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int quad = warp & 3;                              // the TMEM lane quadrant this warp may read
+        const int row = m0 + quad * 32 + lane;
+        const bool row_ok = row < m_valid;
+        mbar_wait(acc_full, 0);                                  // all MMAs done: the stage ring is free, staging aliases it
+        tc::fence_after();
+        unsigned char* staging = base + size_t(warp - 2) * 8192;
+        const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
+        const int ncols = min(p.BN, p.N - n0);
+        const int ce = p.c_bf16 ? 64 : 32;                       // output columns per 128 B staged row
+        const int sw = lane & 7;
+        int ci = 0;
+        for (int c0 = 0; c0 < ncols; c0 += ce, ++ci) {
+            unsigned char* buf = staging + (ci & 1) * 4096;
+            if (ci >= 2) {
+                if (lane == 0) tc::bulk_wait_read<1>();
+                __syncwarp();
+            }
+            unsigned char* myrow = buf + lane * 128;
+            const int halves = p.c_bf16 ? 2 : 1;
+            for (int h = 0; h < halves; ++h) {
+                float v[32];
+                tc::tmem_ld32(tlane + uint32_t(c0 + 32 * h), v);
+                const int jbase = n0 + c0 + 32 * h;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    float x = v[k] * p.alpha;
+                    if (p.act == 1) x = fmaxf(x, 0.0f);
+                    else if (p.act == 2) x = gelu_erf(x);
+                    v[k] = (row_ok && jbase + k < n_valid) ? x : 0.0f;
+                }
+                if (p.c_bf16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 w = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                                   pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                        *reinterpret_cast<uint4*>(myrow + (((4 * h + q) ^ sw) << 4)) = w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                                                   __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+                        *reinterpret_cast<uint4*>(myrow + ((q ^ sw) << 4)) = w;
+                    }
+                }
+            }
+            __syncwarp();
+            if (p.col_stats) {
+                // column sums over this warp's 32 rows (masked rows hold zeros): lane L takes the 32-bit word L of every
+                // staged row -- one fp32 column, or two bf16 columns (the values the next layer will read)
+                float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+                const int chunk = lane >> 2, within = (lane & 3) << 2;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+                    if (p.c_bf16) {
+                        const float a = __uint_as_float(w << 16), c = __uint_as_float(w & 0xffff0000u);
+                        s0 += a; q0 += a * a; s1 += c; q1 += c * c;
+                    } else {
+                        const float a = __uint_as_float(w);
+                        s0 += a; q0 += a * a;
+                    }
+                }
+                float* st = p.col_stats + (size_t(b) * p.parts + size_t(blockIdx.y) * 4 + quad) * size_t(p.N) * 2;
+                if (p.c_bf16) {
+                    const int col = n0 + c0 + 2 * lane;
+                    if (col < p.N) *reinterpret_cast<float2*>(st + size_t(col) * 2) = make_float2(s0, q0);
+                    if (col + 1 < p.N) *reinterpret_cast<float2*>(st + size_t(col + 1) * 2) = make_float2(s1, q1);
+                } else {
+                    const int col = n0 + c0 + lane;
+                    if (col < p.N) *reinterpret_cast<float2*>(st + size_t(col) * 2) = make_float2(s0, q0);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tc::tma_store_3d(&tmap_c, buf, n0 + c0, m0 + quad * 32, b);
+                tc::bulk_commit();
+            }
+        }
+        if (lane == 0) tc::bulk_wait_read<0>();
+        __syncwarp();
+    }
+
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after();
+        tc::tmem_dealloc(tmem_base, uint32_t(p.BN < 32 ? 32 : p.BN));
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled encoder() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    return fn;
+}
+
+// (inner, rows, third) tensor with a (box_inner, box_rows, 1) box and the 128 B swizzle
+int make_map3(CUtensorMap* map, const void* ptr, int dtype, long long inner, long long rows, long long third,
+              long long row_stride_elems, long long third_stride_elems, int box_inner, int box_rows, const char* what,
+              bool atom32 = false) {
+    PFN_encodeTiled enc = encoder();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ISP_ERR_DEVICE; }
+    const int elem = dtype == ISP_DTYPE_BF16 ? 2 : 4;
+    if (third < 1) third = 1;
+    if (third_stride_elems <= 0) third_stride_elems = row_stride_elems * rows;     // a single slice: any legal stride
+    cuuint64_t dims[3] = {cuuint64_t(inner), cuuint64_t(rows), cuuint64_t(third)};
+    cuuint64_t strides[2] = {cuuint64_t(row_stride_elems) * elem, cuuint64_t(third_stride_elems) * elem};
+    cuuint32_t box[3] = {cuuint32_t(box_inner), cuuint32_t(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, dtype == ISP_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("isp_gemm_batched: cuTensorMapEncodeTiled(%s) failed with CUresult %d (inner=%lld rows=%lld third=%lld ld=%lld)",
+                  what, int(r), inner, rows, third, row_stride_elems);
+        return ISP_ERR_INVALID;
+    }
+    return 0;
+}
+
+}  // namespace
+
+int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
+    if (!d || !d->a || !d->b || !d->c) { set_error("isp_gemm_batched: null pointer"); return ISP_ERR_INVALID; }
+    if (d->batch <= 0 || d->M <= 0 || d->N <= 0 || d->K <= 0) { set_error("isp_gemm_batched: sizes must be positive"); return ISP_ERR_INVALID; }
+    if (d->batch > 65535) { set_error("isp_gemm_batched: batch=%d > 65535", d->batch); return ISP_ERR_UNSUPPORTED; }
+    if ((d->dtype_ab != ISP_DTYPE_F32 && d->dtype_ab != ISP_DTYPE_BF16) || (d->dtype_c != ISP_DTYPE_F32 && d->dtype_c != ISP_DTYPE_BF16)) {
+        set_error("isp_gemm_batched: dtypes must be ISP_DTYPE_F32 or ISP_DTYPE_BF16"); return ISP_ERR_INVALID;
+    }
+    const int taps = d->taps > 0 ? d->taps : 1;
+    if (taps > 1 && d->a_mn_major) { set_error("isp_gemm_batched: taps > 1 needs a K-major A"); return ISP_ERR_UNSUPPORTED; }
+    const int elem = d->dtype_ab == ISP_DTYPE_BF16 ? 2 : 4, esz_c = d->dtype_c == ISP_DTYPE_BF16 ? 2 : 4;
+    auto mis = [](const void* ptr, long long s1, long long s2, int e) {
+        return (reinterpret_cast<uintptr_t>(ptr) & 15) || ((s1 * e) & 15) || ((s2 * e) & 15);
+    };
+    if (mis(d->a, d->lda, d->a_batch, elem) || mis(d->b, d->ldb, d->b_batch, elem) || mis(d->b, d->b_tap_stride, 0, elem) ||
+        mis(d->c, d->ldc, d->c_batch, esz_c)) {
+        set_error("isp_gemm_batched: every base pointer and every leading / batch stride must be a multiple of 16 B"); return ISP_ERR_INVALID;
+    }
+    if (d->act < 0 || d->act > 2) { set_error("isp_gemm_batched: act must be 0 (none), 1 (relu) or 2 (gelu)"); return ISP_ERR_INVALID; }
+
+    GemmParams p;
+    p.m_len = d->m_len; p.n_len = d->n_len; p.k_len = d->k_len;
+    p.c = static_cast<unsigned char*>(d->c);
+    p.col_stats = d->col_stats;
+    p.ldc = d->ldc; p.c_batch = d->c_batch;
+    p.batch = d->batch; p.M = d->M; p.N = d->N; p.K = d->K;
+    int bn = d->bn;
+    if (bn == 0) bn = d->N <= 64 ? 64 : (d->N <= 128 ? 128 : (d->N % 256 == 0 || (d->N > 128 && d->N <= 256) ? 256 : 128));
+    if (bn != 64 && bn != 128 && bn != 256) { set_error("isp_gemm_batched: bn must be 0, 64, 128 or 256"); return ISP_ERR_INVALID; }
+    p.BN = bn;
+    p.stages = bn == 128 ? 3 : 4;
+    p.kb = 128 / elem;
+    p.kblocks = (d->K + p.kb - 1) / p.kb;
+    p.taps = taps; p.tap_shift = d->tap_shift;
+    p.a_mn = d->a_mn_major ? 1 : 0; p.b_mn = d->b_mn_major ? 1 : 0;
+    p.a_shared = d->a_batch == 0 ? 1 : 0;
+    p.b_mode = taps > 1 ? 2 : (d->b_batch == 0 ? 1 : 0);
+    if (taps > 1 && d->b_batch != 0) { set_error("isp_gemm_batched: with taps > 1 B is the shared (taps, N, K) filter: b_batch must be 0"); return ISP_ERR_UNSUPPORTED; }
+    p.c_bf16 = d->dtype_c == ISP_DTYPE_BF16 ? 1 : 0;
+    p.act = d->act;
+    p.fill_padding = d->skip_padding ? 0 : 1;
+    p.alpha = d->alpha;
+    const int m_tiles = (d->M + kGM - 1) / kGM;
+    p.parts = m_tiles * 4;
+    const uint32_t fmt = d->dtype_ab == ISP_DTYPE_BF16 ? 1u : 2u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(p.a_mn) << 15) | (uint32_t(p.b_mn) << 16) |
+              (uint32_t(bn >> 3) << 17) | (uint32_t(kGM >> 4) << 24);
+
+    const int me = 128 / elem;          // 64 bf16 / 32 fp32 indices per 128 B
+    CUtensorMap ma, mb, mc;
+    int rc;
+    if (!p.a_mn) rc = make_map3(&ma, d->a, d->dtype_ab, d->K, d->M, p.a_shared ? 1 : d->batch, d->lda, d->a_batch, p.kb, kGM, "A");
+    else         rc = make_map3(&ma, d->a, d->dtype_ab, d->M, d->K, p.a_shared ? 1 : d->batch, d->lda, d->a_batch, me, p.kb, "A", elem == 4);
+    if (rc) return rc;
+    const long long b_third = p.b_mode == 0 ? d->batch : (p.b_mode == 1 ? 1 : taps);
+    const long long b_third_stride = p.b_mode == 0 ? d->b_batch : (p.b_mode == 1 ? 0 : d->b_tap_stride);
+    if (!p.b_mn) rc = make_map3(&mb, d->b, d->dtype_ab, d->K, d->N, b_third, d->ldb, b_third_stride, p.kb, bn, "B");
+    else         rc = make_map3(&mb, d->b, d->dtype_ab, d->N, d->K, b_third, d->ldb, b_third_stride, me, p.kb, "B", elem == 4);
+    if (rc) return rc;
+    rc = make_map3(&mc, d->c, d->dtype_c, d->N, d->M, d->batch, d->ldc, d->c_batch, p.c_bf16 ? 64 : 32, 32, "C");
+    if (rc) return rc;
+
+    const size_t smem = size_t(p.stages) * (kStageA + size_t(bn) * 128) + sizeof(uint64_t) * (2 * kMaxStages + 2) + 1024;
+    const dim3 grid((d->N + bn - 1) / bn, m_tiles, d->batch);
+    cudaError_t e;
+    if (d->dtype_ab == ISP_DTYPE_F32) {
+        e = cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_kernel<tf32>)");
+        gemm_kernel<true><<<grid, kGThreads, smem, stream>>>(ma, mb, mc, p);
+    } else {
+        e = cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_kernel<bf16>)");
+        gemm_kernel<false><<<grid, kGThreads, smem, stream>>>(ma, mb, mc, p);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "gemm_kernel launch");
+    return 0;
+}
+
+}  // namespace isp

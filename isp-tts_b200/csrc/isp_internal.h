@@ -40,6 +40,8 @@ int    length_regulate(const void* x, const int16_t* path, void* out, int dtype,
 int    length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
                                 int B, int T1max, int T2max, int C, cudaStream_t stream);
 
+int    path_from_durations(const int64_t* reps, int16_t* path, int B, int T1max, int T2max, cudaStream_t stream);
+
 int    temporal_average(const float* x, const int64_t* durations, float* out, int B, int C, int T1max, int T2max, cudaStream_t stream);
 int    stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
                       int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, cudaStream_t stream);
@@ -50,6 +52,12 @@ int    ctc_forward(const float* logits, const int64_t* text_len, const int64_t* 
 int    ctc_backward(const float* logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                     float blank_logprob, const float* nll, const float* grad_scale, float* grad_logits, void* ws, size_t ws_bytes,
                     cudaStream_t stream);
+size_t soft_average_workspace_bytes(int B, int C, int T1max, int T2max);
+int    soft_average(const float* x, const float* attn_soft, const int64_t* row_len, float* out, float* colsum, int B, int C,
+                    int T1max, int T2max, void* ws, size_t ws_bytes, cudaStream_t stream);
+int    soft_average_backward(const float* g, const float* x, const float* out, const float* colsum, float* g_soft, int B, int C,
+                             int T1max, int T2max, cudaStream_t stream);
+int    gemm_batched(const isp_gemm_desc* d, cudaStream_t stream);
 int    stage_set_option(const char* key, int value, int* prev);
 
 }  // namespace isp

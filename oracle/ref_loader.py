@@ -81,3 +81,22 @@ def load_alignment():
     spec.loader.exec_module(mod)
     _alignment = mod
     return mod
+
+
+_temporal = None
+
+
+def load_temporal_adaptor():
+    """The reference's temporal_adaptor.py as a module (LengthRegulator, TemporalAverager, generate_soft_path), loaded by
+    file path like alignment.py (its own imports -- tts.modules.transformer, tts.utils -- resolve in this image)."""
+    global _temporal
+    if _temporal is not None:
+        return _temporal
+    load_alignment()                                    # installs the omegaconf stand-in and sys.path
+    path = os.path.join(REFERENCE_ROOT, "tts", "models", "acoustic", "modules", "temporal_adaptor.py")
+    spec = importlib.util.spec_from_file_location("ref_temporal_adaptor", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_temporal_adaptor"] = mod
+    spec.loader.exec_module(mod)
+    _temporal = mod
+    return mod

@@ -119,3 +119,22 @@ def test_prior_matches_reference_shape_and_floor():
     assert p.shape == (2, 9, 5) and p.dtype == np.float32
     assert np.all(p[1, 4:] == 0) and np.all(p[1, :, 3:] == 0)
     assert np.all((p == 0) | (p >= 1e-4))
+
+
+def test_consumers_oracle_against_reference_modules():
+    """oracle/consumers.py against the reference's own LengthRegulator / TemporalAverager outputs (both routes)."""
+    from oracle import consumers as oc
+    g = golden("consumers.npz")
+    T1 = g["attn_soft"].shape[1]
+    out, dec = oc.length_regulate_hard(g["x"], g["durations"], max_len=T1)
+    assert np.array_equal(dec, g["lr_hard_len"]) and np.array_equal(out.astype(np.float32), g["lr_hard"])
+    out, dec = oc.length_regulate_hard(g["x"], g["float_durations"])
+    assert np.array_equal(dec, g["lr_float_len"]) and np.array_equal(out.astype(np.float32), g["lr_float"])
+    out, dec = oc.length_regulate_soft(g["x"], g["durations"], g["attn_soft"], max_len=T1)
+    assert np.array_equal(dec, g["lr_soft_len"]) and np.allclose(out, g["lr_soft"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(oc.temporal_average_hard(g["feat"], g["durations"]), g["avg_hard"], rtol=1e-4, atol=2e-2)   # fp32 running sums
+    assert np.allclose(oc.temporal_average_soft(g["feat"], g["attn_soft"]), g["avg_soft"], rtol=1e-4, atol=1e-3)
+    # the golden path is the argmax of the reference's hard alignment: durations are its histogram
+    for b in range(len(g["mel_len"])):
+        p = g["path"][b, :g["mel_len"][b]]
+        assert np.array_equal(np.bincount(p, minlength=g["durations"].shape[1]), g["durations"][b])
