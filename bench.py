@@ -242,6 +242,36 @@ def run_reference(args, w):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def graph_ms(torch, fn, reps=10):
+    """Device time of one call of `fn` (ms), measured over `reps` replays of a CUDA graph of it: the next-row kernels are tens of
+    microseconds long while their Python wrappers (ctypes, three tensor-map encodes per GEMM) cost about as much on the host, so
+    eager launches would time the host.  Falls back to eager timing if the capture fails."""
+    fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.replay()
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(reps):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+    except Exception as exc:                               # pragma: no cover
+        print(f"[bench] graph capture of a next-row measurement failed ({exc!r}); eager timing", file=sys.stderr, flush=True)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -436,30 +466,50 @@ def run_ours(args, w):
     bwd = None
     if rank == 0 and not args.no_backward:
         from isp_tts_b200.alignment import _scores, loglik_backward_ds
+        from isp_tts_b200.gemm import bgemm
         soft_b, logits_b = _loglik_cuda(q_dev, k_dev, tl_dev, ml_dev, scale, True)
         gen = torch.Generator(device=dev).manual_seed(1)
         g_l = torch.randn(soft_b.shape, device=dev, generator=gen)
         g_s = torch.randn(soft_b.shape, device=dev, generator=gen)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        t_s, t_ds, t_mm = [], [], []
-        for it in range(8):
-            ev[0].record()
-            sc = _scores(q_dev, k_dev)
-            ev[1].record()
-            d_s = loglik_backward_ds(sc, soft_b, g_l, g_s, scale, True, out_dtype=gemm_dtype)
-            ev[2].record()
-            gq = torch.matmul(d_s, k_dev)
-            gk = torch.matmul(d_s.transpose(1, 2), q_dev)
-            ev[3].record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                t_s.append(ev[0].elapsed_time(ev[1])); t_ds.append(ev[1].elapsed_time(ev[2])); t_mm.append(ev[2].elapsed_time(ev[3]))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        box = {}
+
+        def f_scores():
+            box["sc"] = _scores(q_dev, k_dev, tl_dev, ml_dev)                            # isp_gemm_batched, both operands K-major
+
+        def f_ds():
+            box["ds"] = loglik_backward_ds(box["sc"], soft_b, g_l, g_s, scale, True, out_dtype=gemm_dtype)
+
+        def f_grads():
+            box["gq"] = bgemm(box["ds"], k_dev, out_dtype=gemm_dtype, k_len=tl_dev)                  # dQ = dS.K   (K read MN-major)
+            box["gk"] = bgemm(box["ds"].transpose(1, 2), q_dev, out_dtype=gemm_dtype, k_len=ml_dev)  # dK = dS^T.Q (both MN-major)
+
+        def f_lib():
+            box["sc_l"] = torch.bmm(q_dev, k_dev.transpose(1, 2), out_dtype=torch.float32) if gemm_dtype != torch.float32 else torch.matmul(q_dev, k_dev.transpose(1, 2))
+            box["gq_l"] = torch.matmul(box["ds"], k_dev)
+            box["gk_l"] = torch.matmul(box["ds"].transpose(1, 2), q_dev)
+
+        def f_all():
+            f_scores(); f_ds(); f_grads()
+
+        t_s, t_ds, t_mm, t_lib = ([graph_ms(torch, f)] for f in (f_scores, f_ds, f_grads, f_lib))
+        t_all = graph_ms(torch, f_all)
+        sc, d_s, gq, gk, gq_l, gk_l = box["sc"], box["ds"], box["gq"], box["gk"], box["gq_l"], box["gk_l"]
+        gerr = max(float((gq.float() - gq_l.float()).abs().max() / gq_l.float().abs().max()),
+                   float((gk.float() - gk_l.float()).abs().max() / gk_l.float().abs().max()))
+        if gerr > 2e-2:
+            raise RuntimeError("dQ / dK of isp_gemm_batched differ from the library GEMMs: %g" % gerr)
         by_ds = (16 + elem) * B * T1 * T2
-        bwd = {"row": "f-1 backward of the log-likelihood (d attn_logits, d attn_soft -> dQ, dK)",
+        fl_bwd = 3 * 2 * D * B * T1 * T2
+        bwd = {"row": "f-1 backward of the log-likelihood (d attn_logits, d attn_soft -> dQ, dK): no library GEMM",
                "isp_loglik_backward_ds": {"ms": float(np.mean(t_ds)), "algorithmic_bytes": by_ds,
                                           "gbs": by_ds / float(np.mean(t_ds)) / 1e6},
-               "library_gemms_ms": {"scores_QKt": float(np.mean(t_s)), "dQ_and_dK": float(np.mean(t_mm))},
-               "total_ms": float(np.mean(t_s) + np.mean(t_ds) + np.mean(t_mm))}
+               "isp_gemm_batched_ms": {"scores_QKt": float(np.mean(t_s)), "dQ_and_dK": float(np.mean(t_mm))},
+               "library_gemms_same_three_products_ms": float(np.mean(t_lib)),
+               "max_rel_diff_vs_library": gerr, "padded_flops": fl_bwd,
+               "total_ms": float(t_all), "timing": "CUDA graph replay of each part and of the whole backward"}
+        box.clear()
+        del gq_l, gk_l
         # f-3: binarization loss from the path vs the reference's boolean-mask gather on the dense tensors (loss.py:97-105)
         from isp_tts_b200.mas import binarization_loss
         hard_b, dur_b, path_b = mas_forward(logits_b, tl_dev, ml_dev, return_path=True)
@@ -513,7 +563,70 @@ def run_ours(args, w):
         bwd["f-3 length regulator"] = {"isp_length_regulate_ms": float(np.mean(t_ours)), "algorithmic_bytes": by_lr,
                                        "gbs": by_lr / float(np.mean(t_ours)) / 1e6, "torch_reference_ms": float(np.mean(t_ref)),
                                        "shape": f"x ({B}, {T2}, {enc_dim}) fp32 -> ({B}, {T1}, {enc_dim})"}
-        del g_l, g_s, sc, d_s, gq, gk, hard_b, dur_b, path_b, xe, o1, o2, soft_b
+        # f-3, soft route (the recipe's default, core.yaml:148): LengthRegulator as alignment @ x (temporal_adaptor.py:417-419) on the
+        # tcgen05 batched GEMM, and TemporalAverager as one stream over the alignment (:446-449)
+        from isp_tts_b200.soft import soft_average, soft_expand
+        def f_se():
+            box["o3"] = soft_expand(soft_b, xe, frame_len=ml_dev, token_len=tl_dev)
+
+        def f_se_ref():
+            box["o4"] = (xe.transpose(1, 2) @ soft_b.transpose(1, 2)).transpose(1, 2)
+
+        t_ours, t_ref = [graph_ms(torch, f_se)], [graph_ms(torch, f_se_ref)]
+        o3, o4 = box["o3"], box["o4"]
+        serr = float((o3 - o4).abs().max() / o4.abs().max())
+        if serr > 5e-3:
+            raise RuntimeError("soft_expand differs from the reference formula: %g" % serr)
+        by_se = 4 * int((ml * tl).sum()) + 4 * B * T2 * enc_dim + 4 * B * T1 * enc_dim
+        bwd["f-3 soft length regulator"] = {"isp_gemm_batched_ms": float(np.mean(t_ours)), "torch_reference_ms": float(np.mean(t_ref)),
+                                            "algorithmic_bytes": by_se, "gbs": by_se / float(np.mean(t_ours)) / 1e6,
+                                            "padded_flops": 2 * B * T1 * T2 * enc_dim, "max_rel_diff": serr,
+                                            "shape": f"attn_soft ({B}, {T1}, {T2}) fp32 (TF32 products) @ x ({B}, {T2}, {enc_dim})"}
+        feat = torch.rand((B, 2, T1), device=dev, generator=gen) * 200.0
+        def f_sa():
+            box["a1"] = soft_average(feat, soft_b, row_len=ml_dev)
+
+        def f_sa_ref():
+            box["a2"] = feat @ soft_b / (soft_b.sum(dim=1, keepdim=True) + 1e-5)
+
+        t_ours, t_ref = [graph_ms(torch, f_sa)], [graph_ms(torch, f_sa_ref)]
+        a1, a2 = box["a1"], box["a2"]
+        if not torch.allclose(a1, a2, rtol=1e-3, atol=1e-2):
+            raise RuntimeError("soft_average differs from the reference formula")
+        by_sa = 4 * int(ml.sum()) * T2
+        bwd["f-3 soft averager"] = {"isp_soft_average_ms": float(np.mean(t_ours)), "torch_reference_ms": float(np.mean(t_ref)),
+                                    "algorithmic_bytes": by_sa, "gbs": by_sa / float(np.mean(t_ours)) / 1e6}
+        del g_l, g_s, sc, d_s, gq, gk, hard_b, dur_b, path_b, xe, o1, o2, o3, o4, a1, a2, feat, soft_b
+        # f-2: the projection stacks at the recipe's widths (mel 80, text 384, attention_dim 128, kernels 5; 1.7 M parameters) on
+        # this workload's batch shape: fused sm_100a route (stacks.py) against the torch ops under the same autocast
+        from isp_tts_b200 import Aligner
+        al = Aligner(**synth.RECIPE_HP).eval().to(dev)
+        al.attention.gemm_dtype = "bf16"
+        mel_np, txt_np = synth.recipe_inputs(w.seed + 7, B, T1, T2, tl, ml)
+        mel_d, txt_d = torch.from_numpy(mel_np).to(dev), torch.from_numpy(txt_np).to(dev)
+        def f_st():
+            al.attention.fused_stacks = True
+            with torch.no_grad():
+                box["qf"], box["kf"] = al.attention.encode(mel_d, txt_d, ml_dev, tl_dev)
+
+        def f_st_ref():
+            al.attention.fused_stacks = False
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                box["qt"], box["kt"] = al.attention.encode(mel_d, txt_d, ml_dev, tl_dev)
+
+        t_ours, t_ref = [graph_ms(torch, f_st, reps=5)], [graph_ms(torch, f_st_ref, reps=5)]
+        qf, kf, qt, kt = box["qf"], box["kf"], box["qt"], box["kt"]
+        box.clear()
+        qerr = float((qf.float() - qt.float()).abs().max() / qt.float().abs().max())
+        fl_pad = 2 * B * (T2 * (768 * 384 * 5 + 128 * 768) + T1 * (160 * 80 * 5 + 80 * 160 * 5 + 128 * 80))
+        rows_k, rows_q = int(((tl + 127) // 128 * 128).sum()), int(((ml + 127) // 128 * 128).sum())
+        fl_exec = 2 * (rows_k * (768 * 384 * 5 + 128 * 768) + rows_q * (160 * 80 * 5 + 80 * 160 * 5 + 128 * 80))
+        bwd["f-2 projection stacks"] = {"fused_sm100_ms": float(np.mean(t_ours)), "torch_ops_autocast_ms": float(np.mean(t_ref)),
+                                        "padded_flops": fl_pad, "executed_flops_valid_tiles": fl_exec,
+                                        "tflops_executed": fl_exec / float(np.mean(t_ours)) / 1e9, "q_max_rel_diff_vs_torch": qerr,
+                                        "kernels": "isp_prep_channels_last, isp_gemm_batched (implicit-GEMM conv, GELU + norm sums fused), isp_instance_norm_apply",
+                                        "inner_dtype": "float16 activations and weights, bf16 Q / K out"}
+        del al, mel_d, txt_d, qf, kf, qt, kt
         # f-4: forward-sum (CTC) loss and its gradient vs the reference's op sequence on the GPU (loss.py:59-79:
         # F.pad + log_softmax + transpose + nn.CTCLoss(zero_infinity=True)), same logits
         from isp_tts_b200.ctc import attention_ctc_loss
@@ -557,6 +670,9 @@ def run_ours(args, w):
     if bwd is not None:
         bwd["isp_loglik_backward_ds"]["hbm_frac"] = bwd["isp_loglik_backward_ds"]["gbs"] / hbm_peak
         bwd["f-3 length regulator"]["hbm_frac"] = bwd["f-3 length regulator"]["gbs"] / hbm_peak
+        bwd["f-3 soft length regulator"]["hbm_frac"] = bwd["f-3 soft length regulator"]["gbs"] / hbm_peak
+        bwd["f-3 soft averager"]["hbm_frac"] = bwd["f-3 soft averager"]["gbs"] / hbm_peak
+        bwd["f-2 projection stacks"]["tensor_frac_executed"] = bwd["f-2 projection stacks"]["tflops_executed"] / tf_peak
     by_mas = mas_bytes(tl, ml, B, T1, T2)
     by_ll = loglik_bytes(B, T1, T2, D, elem)
     fl_ll = loglik_flops(B, T1, T2, D)

@@ -43,6 +43,7 @@ extern "C" {
 /* element types of the encoded operands of isp_loglik_forward */
 #define ISP_DTYPE_F32  0          /* fp32 in memory, TF32 tensor-core products, fp32 accumulate */
 #define ISP_DTYPE_BF16 1          /* bf16 in memory, fp32 accumulate */
+#define ISP_DTYPE_F16  2          /* fp16 in memory, fp32 accumulate (isp_gemm_batched and its element-wise companions only) */
 
 #define ISP_MAS_MAX_T2   640      /* text tokens per utterance the MAS kernel covers */
 #define ISP_LOGLIK_MAX_T2 512     /* text tokens per utterance the fused GEMM covers (TMEM columns) */
@@ -203,8 +204,8 @@ int    isp_loglik_backward_ds(const float* S, const float* attn_soft, const floa
  * Operand storage:  a_mn_major = 0: A[b][m][k] at a + b*a_batch + m*lda + k   (the contraction index contiguous)
  *                   a_mn_major = 1: A[b][m][k] at a + b*a_batch + k*lda + m   (the row index contiguous: a transposed view)
  *                   b_mn_major = 0: B[b][k][n] at b + b*b_batch + n*ldb + k;  b_mn_major = 1: at b + b*b_batch + k*ldb + n
- * a_batch / b_batch = 0 shares the operand between batch entries.  dtype_ab: ISP_DTYPE_BF16, or ISP_DTYPE_F32 (fp32 in
- * memory, TF32 products).  dtype_c: ISP_DTYPE_F32 or ISP_DTYPE_BF16.  Every pointer and every stride must be a multiple
+ * a_batch / b_batch = 0 shares the operand between batch entries.  dtype_ab: ISP_DTYPE_BF16, ISP_DTYPE_F16, or ISP_DTYPE_F32
+ * (fp32 in memory, TF32 products).  dtype_c: any of the three.  Every pointer and every stride must be a multiple
  * of 16 B.
  * Ragged batches (all optional, DEVICE int64 (batch,)): rows >= m_len[b] and columns >= n_len[b] of C[b] are written as
  * zeros (unless skip_padding, which leaves whole padded tiles untouched); the contraction stops at k_len[b] rounded up to
@@ -214,7 +215,7 @@ int    isp_loglik_backward_ds(const float* S, const float* attn_soft, const floa
  * act: 0 none, 1 ReLU, 2 GELU (erf).  col_stats (optional, fp32 (batch, 4*ceil(M/128), N, 2)): per 32-row slab the
  * column sums of C and of C^2 after masking (the masked-instance-norm statistics, tts/modules/normalization.py:160-208);
  * slabs of padded tiles are not written (pre-zero the buffer).
- * bn: tile width 64 / 128 / 256, 0 = chosen from N. */
+ * bn: tile width up to 256, a multiple of 128 B worth of C's elements (and of B's, when B is MN-major); 0 = chosen from N. */
 typedef struct isp_gemm_desc {
     const void* a; const void* b; void* c;
     const int64_t* m_len; const int64_t* n_len; const int64_t* k_len;
@@ -226,6 +227,19 @@ typedef struct isp_gemm_desc {
     float alpha;
 } isp_gemm_desc;
 int    isp_gemm_batched(const isp_gemm_desc* desc, void* stream);
+
+/* Element-wise companions of the convolution GEMMs of the projection stacks (alignment.py:40-83,118-154,176-187).
+ * isp_prep_channels_last: x (B, C, T) if channels_first else (B, T, C), fp32 or bf16, contiguous -> out (B, T, Cp) in
+ *   out_dtype, zero at t >= len[b] (ConvBlock1D masks its input, alignment.py:75-76; len optional) and in the Cp - C padding
+ *   channels: the K-major activation the implicit-GEMM convolution loads.
+ * isp_instance_norm_apply: masked instance norm (tts/modules/normalization.py:186-206) of a channels-last activation
+ *   y (B, T, C; row stride ld_in) from the column statistics isp_gemm_batched left in `stats` (B, parts, C, 2):
+ *   mean = sum / len, var = sumsq / len - mean^2 (biased), out = ((y - mean) / sqrt(var + eps) * weight + bias) for
+ *   t < len[b], 0 past it.  weight / bias (C) fp32 or NULL.  In place (out == y) is allowed. */
+int    isp_prep_channels_last(const void* x, int in_dtype, int channels_first, const int64_t* len, void* out, int out_dtype,
+                              int B, int C, int T, int Cp, void* stream);
+int    isp_instance_norm_apply(const void* y, int dtype, const float* stats, int parts, const float* weight, const float* bias,
+                               const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, void* stream);
 
 /* Tuning knobs for benchmarks/tests (process-wide, not part of the drop-in contract).
  *   "mas.ring_rows"      rows of logits kept in flight per strip of 128 tokens, 0 = heuristic

@@ -13,11 +13,12 @@ SO_PATH = os.path.join(_PKG, "libisp_tts_b200.so")
 
 ISP_DTYPE_F32 = 0
 ISP_DTYPE_BF16 = 1
+ISP_DTYPE_F16 = 2
 
 EXPORTS = [
     "isp_version", "isp_last_error", "isp_device_check",
     "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_path_from_durations", "isp_temporal_average", "isp_ctc_workspace_bytes", "isp_ctc_forward", "isp_ctc_backward", "isp_mas_status",
-    "isp_stage_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_gemm_batched", "isp_soft_average_workspace_bytes", "isp_soft_average", "isp_soft_average_backward", "isp_set_option",
+    "isp_stage_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_backward_ds", "isp_gemm_batched", "isp_prep_channels_last", "isp_instance_norm_apply", "isp_soft_average_workspace_bytes", "isp_soft_average", "isp_soft_average_backward", "isp_set_option",
 ]
 
 _lib = None
@@ -92,12 +93,25 @@ def load():
     lib.isp_soft_average.restype = c_int
     lib.isp_soft_average_backward.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp]
     lib.isp_soft_average_backward.restype = c_int
+    lib.isp_prep_channels_last.argtypes = [vp, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
+    lib.isp_prep_channels_last.restype = c_int
+    lib.isp_instance_norm_apply.argtypes = [vp, c_int, vp, c_int, vp, vp, vp, vp, c_int, c_int, c_int, c_i64, c_i64, f32, vp]
+    lib.isp_instance_norm_apply.restype = c_int
     lib.isp_gemm_batched.argtypes = [ctypes.POINTER(GemmDesc), vp]
     lib.isp_gemm_batched.restype = c_int
     lib.isp_set_option.argtypes = [ctypes.c_char_p, c_int]
     lib.isp_set_option.restype = c_int
     _lib = lib
     return lib
+
+
+def dtype_code(dtype) -> int:
+    """ISP_DTYPE_* of a torch dtype."""
+    import torch
+    try:
+        return {torch.float32: ISP_DTYPE_F32, torch.bfloat16: ISP_DTYPE_BF16, torch.float16: ISP_DTYPE_F16}[dtype]
+    except KeyError:
+        raise ValueError(f"dtype must be float32, bfloat16 or float16, got {dtype}") from None
 
 
 def check(rc: int, what: str):

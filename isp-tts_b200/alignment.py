@@ -11,7 +11,7 @@ What is different underneath:
     (isp_mas_forward); there is no numba, no CPU route, no device->host check per step;
   * the last 1x1 projection of each stack is evaluated as a matmul that emits the
     (B, T, D) layout the GEMM's TMA loads want (same weights, same state_dict keys).
-The conv stacks themselves are still torch ops ("next").
+
 """
 from __future__ import annotations
 
@@ -27,6 +27,7 @@ from torch import Tensor
 from torch.nn import functional as F
 
 from . import _lib
+from .gemm import bgemm
 from .mas import mas_forward
 
 __all__ = ["stage_operands", "batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
@@ -208,14 +209,10 @@ def stage_operands(q_host: Tensor, k_host: Tensor, text_len: Tensor, mel_len: Te
     return out_q, out_k
 
 
-def _scores(q: Tensor, k: Tensor) -> Tensor:
-    """Unscaled S = Q.K^T in fp32 (a plain library GEMM; bf16 operands keep an fp32 result)."""
-    if q.dtype == torch.float32:
-        return torch.matmul(q, k.transpose(1, 2))
-    try:
-        return torch.bmm(q, k.transpose(1, 2), out_dtype=torch.float32)
-    except TypeError:                                   # older torch: no out_dtype on bmm
-        return torch.matmul(q.float(), k.float().transpose(1, 2))
+def _scores(q: Tensor, k: Tensor, text_len: Tensor | None = None, mel_len: Tensor | None = None) -> Tensor:
+    """Unscaled S = Q.K^T in fp32 for the backward pass: the tcgen05 batched GEMM (isp_gemm_batched), both operands K-major.
+    Tiles of padded frames / tokens are zero-filled without arithmetic (S is exactly 0 there: the operands' padding is 0)."""
+    return bgemm(q, k.transpose(1, 2), m_len=mel_len, n_len=text_len)
 
 
 def loglik_backward_ds(scores: Tensor, soft: Tensor, g_logits: Tensor | None, g_soft: Tensor | None, scale: float,
@@ -248,25 +245,28 @@ def loglik_backward_ds(scores: Tensor, soft: Tensor, g_logits: Tensor | None, g_
 
 
 class _LogLikelihood(torch.autograd.Function):
-    """forward: the fused sm_100a kernel.  backward: the scores are recomputed by a library
-    GEMM, dS comes from the sm_100a kernel behind isp_loglik_backward_ds, dQ = dS.K and dK = dS^T.Q are library GEMMs."""
+    """forward: the fused sm_100a kernel.  backward: three launches of the tcgen05 batched GEMM
+    (isp_gemm_batched) around the one-pass Jacobian kernel (isp_loglik_backward_ds) -- scores S = Q.K^T recomputed,
+    dS from the incoming gradients, dQ = dS.K (K read MN-major), dK = dS^T.Q (both operands MN-major: no transposed copy).
+    No library GEMM anywhere.  The contractions stop at the lengths (K rows >= text_len and Q rows >= mel_len are zero, so
+    nothing is lost); every row of dQ / dK is computed, padded ones included, exactly as autograd would."""
 
     @staticmethod
     def forward(ctx, q, k, text_len, mel_len, scale, prior):
         soft, logits = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior)
-        ctx.save_for_backward(q, k, soft)
+        ctx.save_for_backward(q, k, soft, text_len, mel_len)
         ctx.scale, ctx.prior = scale, prior
         return soft, logits
 
     @staticmethod
     def backward(ctx, g_soft, g_logits):
-        q, k, soft = ctx.saved_tensors
+        q, k, soft, text_len, mel_len = ctx.saved_tensors
         if g_soft is None and g_logits is None:
             return None, None, None, None, None, None
-        qd, kd = q.detach(), k.detach()
-        d_s = loglik_backward_ds(_scores(qd, kd), soft, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
-        gq = torch.matmul(d_s, kd) if ctx.needs_input_grad[0] else None
-        gk = torch.matmul(d_s.transpose(1, 2), qd) if ctx.needs_input_grad[1] else None
+        qd, kd = q.detach().contiguous(), k.detach().contiguous()
+        d_s = loglik_backward_ds(_scores(qd, kd, text_len, mel_len), soft, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
+        gq = bgemm(d_s, kd, out_dtype=q.dtype, k_len=text_len) if ctx.needs_input_grad[0] else None
+        gk = bgemm(d_s.transpose(1, 2), qd, out_dtype=k.dtype, k_len=mel_len) if ctx.needs_input_grad[1] else None
         return gq, gk, None, None, None, None
 
 
@@ -343,8 +343,16 @@ class ConvAttention(nn.Module, _ConfigInit):
         self.mel_dim, self.text_dim = mel_dim, text_dim
         self.scale = attention_dim ** -0.5
         self.attention_prior = attention_prior
-        #: "auto": bf16 operands under autocast, fp32 operands (TF32 products) otherwise; or "fp32" / "bf16"
+        #: "auto": bf16 operands under autocast, else "fp32" = fp32 operands in memory with TF32 tensor-core products (10-bit
+        #: mantissa, fp32 accumulate: within 1e-3 relative of the fp32 reference, tests/test_gpu_loglik.py); or "bf16"
         self.gemm_dtype = "auto"
+        #: projection stacks on the sm_100a kernels (stacks.py) when no gradient is needed: "auto" = in bf16 mode (autocast,
+        #: the recipe's mixed-precision setting) -- in fp32 mode the torch ops run, because TF32 products through two
+        #: convolution layers leave the logits 1e-2 away from the fp32 reference; True = also in fp32 mode; False = never
+        self.fused_stacks = "auto"
+        #: type of the activations and weights inside the fused stacks in bf16 mode: float16 (10-bit mantissa, what the
+        #: reference's fp16 autocast computes its convolutions in, recipes/default.yaml:56) or bfloat16
+        self.stack_dtype = torch.float16
         drop = dropout if dropout and dropout > 0.0 else None
         if isinstance(query_kernel_size, int):
             query_kernel_size = [query_kernel_size] * 2
@@ -371,8 +379,31 @@ class ConvAttention(nn.Module, _ConfigInit):
             return last.forward_tokens_major(x, mask)          # (B, T, D), zero on padded rows
         return last(x, input_mask=mask, output_mask=mask).transpose(1, 2)
 
+    def _mode(self) -> str:
+        mode = self.gemm_dtype
+        if mode == "auto":
+            mode = "bf16" if torch.is_autocast_enabled() else "fp32"
+        return mode
+
+    def _needs_autograd(self, *inputs: Tensor) -> bool:
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in inputs))
+
     def encode(self, queries: Tensor, keys: Tensor, query_len: Tensor, key_len: Tensor):
-        """The two projection stacks (alignment.py:176-187) -> q (B, T1, D), k (B, T2, D)."""
+        """The two projection stacks (alignment.py:176-187) -> q (B, T1, D), k (B, T2, D), zero past the lengths.
+
+        Without gradients (evaluation, alignment extraction) both stacks run on the sm_100a kernels (stacks.py: implicit-GEMM
+        convolutions on the tensor cores with the activation and the norm statistics fused, in the log-likelihood's operand
+        type).  With gradients enabled, or for block configurations the kernels do not cover (batch norm, other activations,
+        channel counts that are not whole 16 B vectors), the torch restatement below runs so that autograd can record it."""
+        from . import stacks
+        dtype = torch.bfloat16 if self._mode() == "bf16" else torch.float32
+        want = self.fused_stacks is True or (self.fused_stacks == "auto" and dtype == torch.bfloat16)
+        if (want and queries.is_cuda and not self._needs_autograd(queries, keys)
+                and stacks.fused_supported(self.key_proj, dtype) and stacks.fused_supported(self.query_proj, dtype)):   # 2-byte types share a rule
+            inner = self.stack_dtype if dtype == torch.bfloat16 else torch.float32
+            k = stacks.project_stack(self.key_proj, keys, key_len, self.text_dim, inner, out_dtype=dtype)
+            q = stacks.project_stack(self.query_proj, queries, query_len, self.mel_dim, inner, out_dtype=dtype)
+            return q, k
         keys = keys.transpose(1, 2) if keys.shape[1] != self.text_dim else keys
         queries = queries.transpose(1, 2) if queries.shape[1] != self.mel_dim else queries
         key_mask = _length_mask(key_len, keys.shape[2]).unsqueeze(1)
@@ -386,10 +417,7 @@ class ConvAttention(nn.Module, _ConfigInit):
         """queries (B, mel_dim, T1) mel, keys (B, text_dim, T2) encoded text, lengths (B,)
         -> (attn_soft, attn_logits), both (B, T1, T2) fp32 (alignment.py:159-208)."""
         q, k = self.encode(queries, keys, query_len, key_len)
-        mode = self.gemm_dtype
-        if mode == "auto":
-            mode = "bf16" if torch.is_autocast_enabled() else "fp32"
-        if mode == "bf16":
+        if self._mode() == "bf16":
             q, k = q.to(torch.bfloat16), k.to(torch.bfloat16)
         else:
             q, k = q.float(), k.float()

@@ -153,6 +153,16 @@ int isp_soft_average_backward(const float* g, const float* x, const float* out, 
     return isp::soft_average_backward(g, x, out, colsum, g_soft, B, C, T1max, T2max, static_cast<cudaStream_t>(stream));
 }
 
+int isp_prep_channels_last(const void* x, int in_dtype, int channels_first, const int64_t* len, void* out, int out_dtype,
+                           int B, int C, int T, int Cp, void* stream) {
+    return isp::prep_channels_last(x, in_dtype, channels_first, len, out, out_dtype, B, C, T, Cp, static_cast<cudaStream_t>(stream));
+}
+
+int isp_instance_norm_apply(const void* y, int dtype, const float* stats, int parts, const float* weight, const float* bias,
+                            const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, void* stream) {
+    return isp::instance_norm_apply(y, dtype, stats, parts, weight, bias, len, out, B, T, C, ld_in, ld_out, eps, static_cast<cudaStream_t>(stream));
+}
+
 int isp_gemm_batched(const isp_gemm_desc* desc, void* stream) { return isp::gemm_batched(desc, static_cast<cudaStream_t>(stream)); }
 
 int isp_set_option(const char* key, int value) {

@@ -51,22 +51,42 @@ struct GemmParams {
     float* col_stats;
     long long ldc, c_batch;              // elements
     int batch, M, N, K;
-    int BN, stages, kb, kblocks;
+    int BN, tmem_cols, stages, kb, kblocks;   // BN: tile width, a multiple of 16 (64 / 32 for an MN-major B), <= 256
     int taps, tap_shift;
     int a_mn, b_mn, a_shared, b_mode;    // b_mode: third TMA coordinate of B = 0: batch, 1: zero, 2: tap
-    int c_bf16, act, fill_padding;
+    int c_bf16, c_f16, act, fill_padding;   // c_bf16: C has 2-byte elements (bf16, or fp16 when c_f16)
     int parts;                           // row partitions of the column statistics: m_tiles * 4
     float alpha;
     uint32_t idesc;
 };
 
-ISP_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU with the exact (erf) form of nn.GELU(), erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. below fp32 rounding of
+// the product): one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner chain instead of erff's branches -- the epilogue of a 128 x 256
+// tile evaluates 256 of these per thread with a single warp per scheduler.
+ISP_DEVINL float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = exp2f(-z * z * 1.4426950408889634f);
+    const float erf_abs = fmaf(-poly * t, e, 1.0f);            // erf(|x| / sqrt 2)
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 ISP_DEVINL uint32_t pack_bf16(float a, float b) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+ISP_DEVINL uint32_t pack_f16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+ISP_DEVINL float f16_lo(uint32_t w) { float f; asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(f) : "r"(w)); return f; }
+ISP_DEVINL float f16_hi(uint32_t w) { float f; asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, hi;}" : "=f"(f) : "r"(w)); return f; }
 
 template <bool TF32>
 __global__ void __launch_bounds__(kGThreads)
@@ -122,7 +142,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tc::prefetch_tmap(&tmap_b);
         tc::prefetch_tmap(&tmap_c);
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, uint32_t(p.BN < 32 ? 32 : p.BN));
+    if (warp == 1) tc::tmem_alloc(tmem_slot, uint32_t(p.tmem_cols));
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
@@ -213,8 +233,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 if (p.c_bf16) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint4 w = make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                                   pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                        const uint4 w = p.c_f16
+                            ? make_uint4(pack_f16(v[8 * q], v[8 * q + 1]), pack_f16(v[8 * q + 2], v[8 * q + 3]),
+                                         pack_f16(v[8 * q + 4], v[8 * q + 5]), pack_f16(v[8 * q + 6], v[8 * q + 7]))
+                            : make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                         pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
                         *reinterpret_cast<uint4*>(myrow + (((4 * h + q) ^ sw) << 4)) = w;
                     }
                 } else {
@@ -236,7 +259,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 for (int r = 0; r < 32; ++r) {
                     const uint32_t w = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
                     if (p.c_bf16) {
-                        const float a = __uint_as_float(w << 16), c = __uint_as_float(w & 0xffff0000u);
+                        const float a = p.c_f16 ? f16_lo(w) : __uint_as_float(w << 16);
+                        const float c = p.c_f16 ? f16_hi(w) : __uint_as_float(w & 0xffff0000u);
                         s0 += a; q0 += a * a; s1 += c; q1 += c * c;
                     } else {
                         const float a = __uint_as_float(w);
@@ -268,7 +292,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc::fence_after();
-        tc::tmem_dealloc(tmem_base, uint32_t(p.BN < 32 ? 32 : p.BN));
+        tc::tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
     }
 }
 
@@ -292,14 +316,14 @@ int make_map3(CUtensorMap* map, const void* ptr, int dtype, long long inner, lon
               bool atom32 = false) {
     PFN_encodeTiled enc = encoder();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ISP_ERR_DEVICE; }
-    const int elem = dtype == ISP_DTYPE_BF16 ? 2 : 4;
+    const int elem = dtype == ISP_DTYPE_F32 ? 4 : 2;
     if (third < 1) third = 1;
     if (third_stride_elems <= 0) third_stride_elems = row_stride_elems * rows;     // a single slice: any legal stride
     cuuint64_t dims[3] = {cuuint64_t(inner), cuuint64_t(rows), cuuint64_t(third)};
     cuuint64_t strides[2] = {cuuint64_t(row_stride_elems) * elem, cuuint64_t(third_stride_elems) * elem};
     cuuint32_t box[3] = {cuuint32_t(box_inner), cuuint32_t(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, dtype == ISP_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+    CUresult r = enc(map, dtype == ISP_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (dtype == ISP_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 3,
                      const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -317,12 +341,12 @@ int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
     if (!d || !d->a || !d->b || !d->c) { set_error("isp_gemm_batched: null pointer"); return ISP_ERR_INVALID; }
     if (d->batch <= 0 || d->M <= 0 || d->N <= 0 || d->K <= 0) { set_error("isp_gemm_batched: sizes must be positive"); return ISP_ERR_INVALID; }
     if (d->batch > 65535) { set_error("isp_gemm_batched: batch=%d > 65535", d->batch); return ISP_ERR_UNSUPPORTED; }
-    if ((d->dtype_ab != ISP_DTYPE_F32 && d->dtype_ab != ISP_DTYPE_BF16) || (d->dtype_c != ISP_DTYPE_F32 && d->dtype_c != ISP_DTYPE_BF16)) {
-        set_error("isp_gemm_batched: dtypes must be ISP_DTYPE_F32 or ISP_DTYPE_BF16"); return ISP_ERR_INVALID;
+    if (d->dtype_ab < ISP_DTYPE_F32 || d->dtype_ab > ISP_DTYPE_F16 || d->dtype_c < ISP_DTYPE_F32 || d->dtype_c > ISP_DTYPE_F16) {
+        set_error("isp_gemm_batched: dtypes must be ISP_DTYPE_F32, ISP_DTYPE_BF16 or ISP_DTYPE_F16"); return ISP_ERR_INVALID;
     }
     const int taps = d->taps > 0 ? d->taps : 1;
     if (taps > 1 && d->a_mn_major) { set_error("isp_gemm_batched: taps > 1 needs a K-major A"); return ISP_ERR_UNSUPPORTED; }
-    const int elem = d->dtype_ab == ISP_DTYPE_BF16 ? 2 : 4, esz_c = d->dtype_c == ISP_DTYPE_BF16 ? 2 : 4;
+    const int elem = d->dtype_ab == ISP_DTYPE_F32 ? 4 : 2, esz_c = d->dtype_c == ISP_DTYPE_F32 ? 4 : 2;
     auto mis = [](const void* ptr, long long s1, long long s2, int e) {
         return (reinterpret_cast<uintptr_t>(ptr) & 15) || ((s1 * e) & 15) || ((s2 * e) & 15);
     };
@@ -338,11 +362,27 @@ int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
     p.col_stats = d->col_stats;
     p.ldc = d->ldc; p.c_batch = d->c_batch;
     p.batch = d->batch; p.M = d->M; p.N = d->N; p.K = d->K;
+    // Tile width: as few column tiles as 256 TMEM columns allow, each as narrow as N permits (UMMA N is any multiple of 16),
+    // so that N = 160, 200 or 384 waste nothing; an MN-major B arrives in 128 B-wide boxes, hence multiples of 64 / 32.
+    // and the epilogue stores whole 128 B-wide chunks (32 fp32 / 64 two-byte columns), which must not reach into the next tile
+    const int n_unit = std::max(d->b_mn_major ? 128 / elem : 16, 128 / esz_c);
     int bn = d->bn;
-    if (bn == 0) bn = d->N <= 64 ? 64 : (d->N <= 128 ? 128 : (d->N % 256 == 0 || (d->N > 128 && d->N <= 256) ? 256 : 128));
-    if (bn != 64 && bn != 128 && bn != 256) { set_error("isp_gemm_batched: bn must be 0, 64, 128 or 256"); return ISP_ERR_INVALID; }
+    if (bn == 0) {
+        const int nt = (d->N + 255) / 256;
+        bn = ((d->N + nt - 1) / nt + n_unit - 1) / n_unit * n_unit;
+    }
+    if (bn < 16 || bn > 256 || bn % n_unit) { set_error("isp_gemm_batched: bn must be 0 or a multiple of %d up to 256", n_unit); return ISP_ERR_INVALID; }
     p.BN = bn;
-    p.stages = bn == 128 ? 3 : 4;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < bn) p.tmem_cols <<= 1;
+    // Ring depth: no deeper than the longest contraction needs (short ones then leave room for three or four CTAs per SM,
+    // which is what hides the per-tile latencies of a memory-bound GEMM), at most four, and at least the 32 KB of staging
+    const int kiters_max = taps * ((d->K + 128 / elem - 1) / (128 / elem));
+    p.stages = std::max(2, std::min(4, kiters_max));
+    // keep two CTAs on an SM (<= 108 KB each) unless the tile is the wide, long, compute-bound one: the epilogue of one then
+    // runs under the loads and MMAs of the other
+    const bool heavy = bn == 256 && kiters_max >= 16;
+    while (!heavy && p.stages > 2 && size_t(p.stages) * (kStageA + size_t(bn) * 128) > 108 * 1024) --p.stages;
     p.kb = 128 / elem;
     p.kblocks = (d->K + p.kb - 1) / p.kb;
     p.taps = taps; p.tap_shift = d->tap_shift;
@@ -350,13 +390,14 @@ int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
     p.a_shared = d->a_batch == 0 ? 1 : 0;
     p.b_mode = taps > 1 ? 2 : (d->b_batch == 0 ? 1 : 0);
     if (taps > 1 && d->b_batch != 0) { set_error("isp_gemm_batched: with taps > 1 B is the shared (taps, N, K) filter: b_batch must be 0"); return ISP_ERR_UNSUPPORTED; }
-    p.c_bf16 = d->dtype_c == ISP_DTYPE_BF16 ? 1 : 0;
+    p.c_bf16 = d->dtype_c == ISP_DTYPE_F32 ? 0 : 1;
+    p.c_f16 = d->dtype_c == ISP_DTYPE_F16 ? 1 : 0;
     p.act = d->act;
     p.fill_padding = d->skip_padding ? 0 : 1;
     p.alpha = d->alpha;
     const int m_tiles = (d->M + kGM - 1) / kGM;
     p.parts = m_tiles * 4;
-    const uint32_t fmt = d->dtype_ab == ISP_DTYPE_BF16 ? 1u : 2u;
+    const uint32_t fmt = d->dtype_ab == ISP_DTYPE_BF16 ? 1u : (d->dtype_ab == ISP_DTYPE_F16 ? 0u : 2u);   // UMMA F16 = 0, BF16 = 1, TF32 = 2
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(p.a_mn) << 15) | (uint32_t(p.b_mn) << 16) |
               (uint32_t(bn >> 3) << 17) | (uint32_t(kGM >> 4) << 24);
 

@@ -19,11 +19,7 @@ ACT = {None: 0, "linear": 0, "none": 0, "relu": 1, "gelu": 2}
 
 
 def _dt(t: torch.Tensor) -> int:
-    if t.dtype == torch.bfloat16:
-        return _lib.ISP_DTYPE_BF16
-    if t.dtype == torch.float32:
-        return _lib.ISP_DTYPE_F32
-    raise ValueError(f"operands must be float32 or bfloat16, got {t.dtype}")
+    return _lib.dtype_code(t.dtype)
 
 
 def _operand(t: torch.Tensor, cd: int):
@@ -87,7 +83,7 @@ def bgemm(x: torch.Tensor, y: torch.Tensor, *, out_dtype: torch.dtype = torch.fl
     if yo.shape[1] != K:
         raise ValueError(f"shape mismatch: {tuple(x.shape)} @ {tuple(y.shape)}")
     N = yo.shape[2]
-    esz_c = 2 if out_dtype == torch.bfloat16 else 4
+    esz_c = 4 if out_dtype == torch.float32 else 2
     ldc = (N * esz_c + 15) // 16 * 16 // esz_c
     if out is None:
         buf = torch.empty((batch, M, ldc), dtype=out_dtype, device=dev)
@@ -105,7 +101,7 @@ def bgemm(x: torch.Tensor, y: torch.Tensor, *, out_dtype: torch.dtype = torch.fl
     d.a_batch, d.b_batch, d.c_batch = a_b, b_b, (buf.stride(0) if batch > 1 else M * ldc)
     d.b_tap_stride = 0
     d.batch, d.M, d.N, d.K = batch, M, N, K
-    d.dtype_ab, d.dtype_c = _dt(xo), (_lib.ISP_DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32)
+    d.dtype_ab, d.dtype_c = _dt(xo), _lib.dtype_code(out_dtype)
     d.a_mn_major, d.b_mn_major = a_mn, b_mn
     d.taps, d.tap_shift, d.act, d.bn, d.skip_padding = 1, 0, ACT[act], bn, 0
     d.alpha = float(alpha)
@@ -135,7 +131,7 @@ def conv1d_channels_last(x: torch.Tensor, w_taps: torch.Tensor, lengths=None, *,
     if (Cin * esz) % 16:
         raise ValueError("Cin * element size must be a multiple of 16 B")
     B, T, _ = x.shape
-    esz_c = 2 if out_dtype == torch.bfloat16 else 4
+    esz_c = 4 if out_dtype == torch.float32 else 2
     ldc = (Cout * esz_c + 15) // 16 * 16 // esz_c
     buf = torch.empty((B, T, ldc), dtype=out_dtype, device=dev)
     stats = torch.zeros((B, 4 * ((T + 127) // 128), Cout, 2), dtype=torch.float32, device=dev) if col_stats else None
@@ -148,7 +144,7 @@ def conv1d_channels_last(x: torch.Tensor, w_taps: torch.Tensor, lengths=None, *,
     d.a_batch, d.b_batch, d.c_batch = x.stride(0), 0, T * ldc
     d.b_tap_stride = Cout * Cin
     d.batch, d.M, d.N, d.K = B, T, Cout, Cin
-    d.dtype_ab, d.dtype_c = _dt(x), (_lib.ISP_DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32)
+    d.dtype_ab, d.dtype_c = _dt(x), _lib.dtype_code(out_dtype)
     d.a_mn_major, d.b_mn_major = 0, 0
     d.taps, d.tap_shift, d.act, d.bn, d.skip_padding = k, -(k // 2), ACT[act], bn, 0
     d.alpha = 1.0

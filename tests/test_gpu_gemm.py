@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 # bf16 operands are compared at the operands' precision (inputs rounded to bf16 first): what is left is fp32 accumulation
 # order.  fp32 operands go through TF32 products (10-bit mantissa): 2e-3 of the row's scale.
-TOL = {torch.bfloat16: 2e-5, torch.float32: 3e-3}
+TOL = {torch.bfloat16: 2e-5, torch.float16: 2e-5, torch.float32: 3e-3}
 
 
 def rnd(shape, dev, dtype, seed):
@@ -26,7 +26,7 @@ def check(got, ref, dtype, what, out_bf16=False):
     assert err <= tol, f"{what}: relative error {err:.3e} > {tol:.1e}"
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("tb", [False, True])
 @pytest.mark.parametrize("shape", [(3, 200, 128, 1000), (2, 1000, 384, 200), (4, 130, 72, 40), (1, 128, 256, 64), (2, 77, 520, 136)])
@@ -43,7 +43,7 @@ def test_layouts_against_float64(cuda_device, dtype, ta, tb, shape):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
 def test_tile_widths_and_shared_operand(cuda_device, dtype, bn):
     B, M, N, K = 3, 260, 200, 96
     a = rnd((B, M, K), cuda_device, dtype, 3)
@@ -99,13 +99,20 @@ def test_activation_and_column_statistics(cuda_device, act):
     g64 = got.double()
     assert torch.allclose(s[..., 0], g64.sum(dim=1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(s[..., 1], (g64 * g64).sum(dim=1), rtol=1e-4, atol=1e-2)
+    a16, w16 = a.to(torch.float16), w.to(torch.float16)
+    got16, stats16 = bgemm(a16, w16.t(), m_len=ml, act=act, out_dtype=torch.float16, col_stats=True)
+    assert got16.dtype == torch.float16
+    check(got16, ref, torch.float16, act + " fp16", out_bf16=True)
+    s = stats16.double().sum(dim=1)
+    assert torch.allclose(s[..., 0], got16.double().sum(dim=1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[..., 1], (got16.double() ** 2).sum(dim=1), rtol=1e-4, atol=1e-2)
     got32, stats32 = bgemm(a, w.t(), m_len=ml, act=act, col_stats=True)
     s = stats32.double().sum(dim=1)
     assert torch.allclose(s[..., 0], got32.double().sum(dim=1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(s[..., 1], (got32.double() ** 2).sum(dim=1), rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
 @pytest.mark.parametrize("cfg", [(3, 200, 384, 768, 5), (2, 333, 80, 160, 5), (2, 150, 160, 80, 3), (2, 64, 768, 128, 1)])
 def test_implicit_convolution_against_conv1d(cuda_device, dtype, cfg):
     """alignment.py:58-62: Conv1d(kernel k, padding (k - 1) / 2, no bias) on the masked input, channels-last here."""
