@@ -300,9 +300,21 @@ def run_ours(args, w):
     gemm_dtype = torch.bfloat16 if args.gemm == "bf16" else torch.float32
     elem = 2 if args.gemm == "bf16" else 4
     B, T1, T2, D = w.batch, w.t1max, w.t2max, w.dim
-    # every rank owns a different batch of the same law (utterance sharding, weak scaling)
-    tl, ml = synth.lengths(B, T2, T1, w.ragged, w.seed + 1000 * rank)
-    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, w.seed + 1 + 1000 * rank)
+    strong = w.name.startswith("cfg5")
+    if strong:
+        # ONE global batch, the same on every rank, dealt to the ranks by cell count (sharding.balanced_assignment): strong scaling
+        from isp_tts_b200 import sharding
+        tl_g, ml_g = synth.lengths(B, T2, T1, w.ragged, w.seed)
+        mine = sharding.balanced_assignment(tl_g, ml_g, world)[rank]
+        global_B, global_cells = B, int((tl_g * ml_g).sum())
+        tl, ml = tl_g[mine].copy(), ml_g[mine].copy()
+        B = len(mine)
+        q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, w.seed + 1 + 1000 * rank)
+    else:
+        # every rank owns a different batch of the same law (utterance sharding, weak scaling)
+        tl, ml = synth.lengths(B, T2, T1, w.ragged, w.seed + 1000 * rank)
+        q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, w.seed + 1 + 1000 * rank)
+        global_B, global_cells = world * B, None
     scale = D ** -0.5
     q_host = torch.from_numpy(q).to(gemm_dtype).pin_memory()
     k_host = torch.from_numpy(k).to(gemm_dtype).pin_memory()
@@ -434,6 +446,24 @@ def run_ours(args, w):
         e2.record()
         barrier()
     e2e_ms = max_over_ranks(s2.elapsed_time(e2))
+    # The platform's ceiling for that leg: the same number of bytes per step as ONE plain pinned cudaMemcpyAsync on the copy
+    # engine, all ranks at once, nothing else running (what the host side of the PCIe tree gives N GPUs together)
+    ceil_bytes = int((ml.sum() + tl.sum()) * D * q_host.element_size()) if args.e2e_copy == "staged" else \
+        q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size()
+    flat_host = q_host.view(-1)[: ceil_bytes // q_host.element_size()]
+    flat_dev = torch.empty_like(flat_host, device=dev)
+    for _ in range(2):
+        flat_dev.copy_(flat_host, non_blocking=True)
+    barrier()
+    s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s3.record()
+    for _ in range(10):
+        flat_dev.copy_(flat_host, non_blocking=True)
+    e3.record()
+    barrier()
+    ceil_ms = max_over_ranks(s3.elapsed_time(e3)) / 10
+    link_ceiling_gbs = flat_host.numel() * flat_host.element_size() * world / ceil_ms / 1e6
+    del flat_dev
     # durations must be what the resident path produced
     ref_dur = step_resident().cpu()
     torch.cuda.synchronize()
@@ -450,15 +480,19 @@ def run_ours(args, w):
         from isp_tts_b200 import sharding
         dur_dev = step_resident()
         gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sharding.gather_durations(dur_dev, t2max=T2, counts=[B] * world)           # warm-up (NCCL communicator, buffers)
+        counts = [len(a) for a in sharding.balanced_assignment(tl_g, ml_g, world)] if strong else [B] * world
+        off = sum(counts[:rank])
+        sharding.gather_durations(dur_dev, t2max=T2, counts=counts)           # warm-up (NCCL communicator, buffers)
         gs_.record()
-        full = sharding.gather_durations(dur_dev, t2max=T2, counts=[B] * world)
+        full = sharding.gather_durations(dur_dev, t2max=T2, counts=counts)
         ge_.record()
         torch.cuda.synchronize()
         frames = torch.tensor([int(ml.sum())], dtype=torch.int64, device=dev)
         dist.all_reduce(frames)
-        if tuple(full.shape) != (world * B, T2) or int(full.sum()) != int(frames.item()) or not torch.equal(full[rank * B:(rank + 1) * B], dur_dev):
+        if tuple(full.shape) != (sum(counts), T2) or int(full.sum()) != int(frames.item()) or not torch.equal(full[off:off + B], dur_dev):
             raise RuntimeError("gathered durations do not match the ranks' own")
+        if strong and int(full.sum()) != int(ml_g.sum()):
+            raise RuntimeError("gathered durations of the global batch do not sum to its mel lengths")
         gather = {"collective": "ncclAllGather of durations (B_local, T2max) int64 via torch.distributed", "ms": gs_.elapsed_time(ge_),
                   "bytes_per_rank": int(dur_dev.numel() * 8), "shape": list(full.shape)}
 
@@ -722,8 +756,8 @@ def run_ours(args, w):
         cpu["reference_cpu_route_mas"] = {"ms": min(route) * 1e3, "what": "attn_logits.cpu().numpy() -> b_mas -> torch.from_numpy(...).to(device) (alignment.py:305-312)"}
         del lg, out
 
-    utts = world * B * args.steps
-    valid_cells = float((tl * ml).sum()) * world * args.steps
+    utts = global_B * args.steps
+    valid_cells = float(global_cells if strong else (tl * ml).sum() * world) * args.steps
     if args.e2e_copy == "staged":
         h2d = int((ml.sum() + tl.sum()) * D * q_host.element_size()) + 16 * B
     else:
@@ -731,18 +765,24 @@ def run_ours(args, w):
     out = {
         "metric": METRIC, "value": utts / (total_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 GEMM operands; f32 accumulate, epilogue and MAS" if elem == 2 else "tf32 GEMM products; f32 elsewhere",
+        "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "bf16 GEMM operands; f32 accumulate, epilogue and MAS" if elem == 2 else "tf32 GEMM products; f32 elsewhere",
         "data": "synthetic",
         "config": {**base_config(w, tl, ml),
-                   "sharding": f"by utterance, {world} rank(s), no collective on the data path",
+                   "sharding": (f"one global batch of {global_B} utterances dealt to {world} rank(s) by cell count (longest first), "
+                                f"{B} on rank 0; no collective on the data path") if strong else
+                               f"by utterance, {world} rank(s), no collective on the data path",
                    "launch": launch if launch != "graph" else "CUDA graph replay of the step (isp_loglik_forward + isp_mas_forward)",
                    "l2": "per-step working set (operands + 3 dense outputs) = %.0f MB > 126 MB L2; no explicit flush" % (
                        (by_ll + 2 * B * T1 * T2) / 1e6)},
         "valid_cells_per_s": valid_cells / (total_ms / 1e3),
-        "padded_cells_per_s": world * B * T1 * T2 * args.steps / (total_ms / 1e3),
+        "padded_cells_per_s": global_B * T1 * T2 * args.steps / (total_ms / 1e3),
         "roofline": roofline, "roofline_kernels": roofline_all, "kernels": kern, "cpu_baseline": cpu,
         "e2e": {"value": utts / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(dur_host.numel() * 8) + (2 * B * T1 * T2 if hard_hosts is not None else 0), "ms_per_step": e2e_ms / args.steps,
+                "h2d_gbs_all_ranks": h2d * world / (e2e_ms / args.steps) / 1e6,
+                "link_ceiling_gbs": link_ceiling_gbs,
+                "link_ceiling": "aggregate H2D rate of plain pinned cudaMemcpyAsync of the same bytes on all ranks at once, nothing else running",
                 "api": ("isp_stage_operands (valid rows only over PCIe) + " if args.e2e_copy == "staged" else "")
                        + "isp_loglik_forward + isp_mas_forward through isp_tts_b200.  In: pinned host Q, K (already cast to the GEMM's "
                        + ("bf16" if elem == 2 else "fp32") + " on the host, outside the timed region) and int64 lengths.  Out: the int64 durations"

@@ -30,6 +30,8 @@ WORKLOADS = {
     "cfg3": Workload("cfg3: batch 256 ragged LJSpeech-shaped, <=200 tok x <=1000 fr", 256, 200, 1000, True, 1237),
     "cfg3d": Workload("cfg3d: batch 256 dense 200 tok x 1000 fr", 256, 200, 1000, False, 1237),
     "cfg4": Workload("cfg4: long-form batch 16, 512 tok x 4096 fr", 16, 512, 4096, False, 1238),
+    # BASELINE.json configs[4]: ONE global batch (64..4096 utterances, --batch) sharded by utterance across the ranks
+    "cfg5": Workload("cfg5: one global batch of 1024 ragged utterances sharded across the ranks, <=200 tok x <=1000 fr", 1024, 200, 1000, True, 1239),
 }
 
 
