@@ -215,7 +215,7 @@ int    isp_loglik_backward_ds(const float* S, const float* attn_soft, const floa
  * act: 0 none, 1 ReLU, 2 GELU (erf).  col_stats (optional, fp32 (batch, 4*ceil(M/128), N, 2)): per 32-row slab the
  * column sums of C and of C^2 after masking (the masked-instance-norm statistics, tts/modules/normalization.py:160-208);
  * slabs of padded tiles are not written (pre-zero the buffer).
- * bn: tile width up to 256, a multiple of 128 B worth of C's elements (and of B's, when B is MN-major); 0 = chosen from N. */
+ * bn: tile width up to 256, a multiple of 16 (of 128 B worth of B's elements when B is MN-major); 0 = chosen from N. */
 typedef struct isp_gemm_desc {
     const void* a; const void* b; void* c;
     const int64_t* m_len; const int64_t* n_len; const int64_t* k_len;
@@ -225,6 +225,7 @@ typedef struct isp_gemm_desc {
     int32_t dtype_ab, dtype_c, a_mn_major, b_mn_major;
     int32_t taps, tap_shift, act, bn, skip_padding;
     float alpha;
+    void* trace;      /* debug only, normally NULL: device int64 (CTAs, 8), SM-clock stamps of each CTA's phases (tools/gemm_trace.py) */
 } isp_gemm_desc;
 int    isp_gemm_batched(const isp_gemm_desc* desc, void* stream);
 

@@ -34,7 +34,7 @@ class GemmDesc(ctypes.Structure):
                 ("batch", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
                 ("dtype_ab", ctypes.c_int32), ("dtype_c", ctypes.c_int32), ("a_mn_major", ctypes.c_int32), ("b_mn_major", ctypes.c_int32),
                 ("taps", ctypes.c_int32), ("tap_shift", ctypes.c_int32), ("act", ctypes.c_int32), ("bn", ctypes.c_int32),
-                ("skip_padding", ctypes.c_int32), ("alpha", ctypes.c_float)]
+                ("skip_padding", ctypes.c_int32), ("alpha", ctypes.c_float), ("trace", ctypes.c_void_p)]
 
 
 class IspError(RuntimeError):

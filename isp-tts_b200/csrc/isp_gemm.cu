@@ -13,9 +13,12 @@
 //               the 128 B swizzle) into a ring of `stages` buffers guarded by full / empty mbarriers.
 //   warp 1      owns TMEM (BN fp32 columns x 128 lanes); one lane issues 4 tcgen05.mma per stage (kind::f16 for bf16
 //               operands, kind::tf32 for fp32 operands) and releases the stage with tcgen05.commit.
-//   warps 2-5   epilogue: tcgen05.ld of 32 accumulator columns per step, alpha / activation / ragged masks in
-//               registers, the 32 x 128 B chunk staged in shared memory (swizzled, conflict-free) and written with one
-//               TMA store per chunk (coalesced, clipped at the tensor's bounds by the hardware).
+//   warps 2-9   epilogue, two warps per TMEM lane quadrant taking alternate column chunks: tcgen05.ld of 32 accumulator
+//               columns per step, alpha / activation / ragged masks in registers, the 32 x 128 B chunk transposed through
+//               shared memory (swizzled, conflict-free) so that every global store instruction writes four whole 128 B rows.
+//               (Measured and dropped: one TMA store per chunk -- the async-proxy fence and the single issuing lane made a
+//               chunk cost ~1 us of latency per warp; and a persistent CTA per SM with two TMEM accumulators -- four
+//               epilogue warps per SM cannot keep up with the stores: scores 87 -> 158 us, stacks 0.93 -> 1.28 ms.)
 // Operands may be K-major (the contraction index contiguous) or MN-major (the row / column index contiguous): the
 // second is a different TMA box and shared-memory descriptor (leading byte offset between 128 B-wide chunks), so
 // transposed uses of a tensor (dS^T, x as (T2, C)) need no copy.  Ragged batches: tiles past m_len[b] / n_len[b] are
@@ -39,7 +42,8 @@ namespace isp {
 namespace {
 
 constexpr int kGM = 128;                 // tile rows = UMMA M
-constexpr int kGThreads = 192;
+constexpr int kEpiWarps = 8;              // two per TMEM lane quadrant, alternating column chunks
+constexpr int kGThreads = 32 * (2 + kEpiWarps);
 constexpr int kStageA = kGM * 128;       // bytes of A per stage
 constexpr int kMaxStages = 6;
 
@@ -49,6 +53,7 @@ struct GemmParams {
     const int64_t* k_len;
     unsigned char* c;
     float* col_stats;
+    long long* trace;                    // debug: 8 SM-clock stamps per CTA (see isp_gemm_desc.trace), or nullptr
     long long ldc, c_batch;              // elements
     int batch, M, N, K;
     int BN, tmem_cols, stages, kb, kblocks;   // BN: tile width, a multiple of 16 (64 / 32 for an MN-major B), <= 256
@@ -65,12 +70,13 @@ struct GemmParams {
 // tile evaluates 256 of these per thread with a single warp per scheduler.
 ISP_DEVINL float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
-    const float e = exp2f(-z * z * 1.4426950408889634f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
     const float erf_abs = fmaf(-poly * t, e, 1.0f);            // erf(|x| / sqrt 2)
     return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
@@ -88,10 +94,12 @@ ISP_DEVINL uint32_t pack_f16(float a, float b) {
 ISP_DEVINL float f16_lo(uint32_t w) { float f; asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(f) : "r"(w)); return f; }
 ISP_DEVINL float f16_hi(uint32_t w) { float f; asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, hi;}" : "=f"(f) : "r"(w)); return f; }
 
-template <bool TF32>
+// ACT: 0 none, 1 ReLU, 2 GELU.  CT: element type of C, 0 fp32, 1 bf16, 2 fp16.  Compile-time so that the epilogue's inner loops
+// carry no per-element decisions (with run-time switches a 32 x 32 chunk cost ~800 warp instructions and the sixteen epilogue
+// warps of an SM were issue-bound: 16 us per tile pair on the f-1 shapes).
+template <bool TF32, int ACT, int CT>
 __global__ void __launch_bounds__(kGThreads)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * p.BN, m0 = blockIdx.y * kGM, b = blockIdx.z;
@@ -134,19 +142,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         return;
     }
 
+    const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    long long* tr = p.trace ? p.trace + size_t(cta_lin) * 8 : nullptr;
+    if (tr && threadIdx.x == 0) tr[0] = clock64();
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_mbar_init();
         tc::prefetch_tmap(&tmap_a);
         tc::prefetch_tmap(&tmap_b);
-        tc::prefetch_tmap(&tmap_c);
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, uint32_t(p.tmem_cols));
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tr && threadIdx.x == 0) tr[1] = clock64();             // barriers, tensor-map prefetch, TMEM allocation, CTA sync
 
     const int me = TF32 ? 32 : 64;                 // M/N indices per 128 B row of an MN-major operand
     const uint32_t lbo = uint32_t(p.kb) * 128u;    // bytes between two such chunks (one TMA box each)
@@ -173,6 +184,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 } else {
                     for (int c = 0; c < p.BN / me; ++c) tc::tma_load_3d(sb + c * lbo, &tmap_b, n0 + c * me, kbi * p.kb, third, &full[s]);
                 }
+                if (tr && it == 0) tr[2] = clock64();            // first stage issued
             }
         }
     } else if (warp == 1) {
@@ -183,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 const uint32_t ph = uint32_t(it / p.stages) & 1u;
                 mbar_wait(&full[s], ph);
                 tc::fence_after();
+                if (tr && it == 0) tr[3] = clock64();            // first stage landed
                 const uint32_t sa = smem_u32(base + size_t(s) * stage_bytes);
                 const uint32_t sb = sa + kStageA;
 #pragma unroll
@@ -197,70 +210,80 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 tc::umma_commit(&empty[s]);
             }
             tc::umma_commit(acc_full);
+            if (tr) tr[4] = clock64();                           // every MMA issued
         }
     } else {
         // ================================ epilogue ================================
+        constexpr int ce = CT == 0 ? 32 : 64;                    // output columns per 128 B staged row
+        constexpr int esz = CT == 0 ? 4 : 2;
         const int quad = warp & 3;                              // the TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                        // 0: chunks 0, 2, 4, ...   1: chunks 1, 3, 5, ...
         const int row = m0 + quad * 32 + lane;
         const bool row_ok = row < m_valid;
         mbar_wait(acc_full, 0);                                  // all MMAs done: the stage ring is free, staging aliases it
         tc::fence_after();
-        unsigned char* staging = base + size_t(warp - 2) * 8192;
+        if (tr && threadIdx.x == 64) tr[5] = clock64();          // accumulator complete
+        unsigned char* buf = base + size_t(warp - 2) * 4096;     // 32 rows x 128 B, 16 B chunks XOR-swizzled by (row & 7)
         const uint32_t tlane = tmem_base + (uint32_t(quad * 32) << 16);
         const int ncols = min(p.BN, p.N - n0);
-        const int ce = p.c_bf16 ? 64 : 32;                       // output columns per 128 B staged row
         const int sw = lane & 7;
-        int ci = 0;
-        for (int c0 = 0; c0 < ncols; c0 += ce, ++ci) {
-            unsigned char* buf = staging + (ci & 1) * 4096;
-            if (ci >= 2) {
-                if (lane == 0) tc::bulk_wait_read<1>();
-                __syncwarp();
-            }
-            unsigned char* myrow = buf + lane * 128;
-            const int halves = p.c_bf16 ? 2 : 1;
-            for (int h = 0; h < halves; ++h) {
+        // store side: lane -> (row rb + 4 * it, 16 B chunk q_st) of the staged block; four whole rows per instruction
+        const int rb = lane >> 3, q_st = lane & 7;
+        const int rows_here = min(32, p.M - (m0 + quad * 32));   // rows of this warp's slab inside the tensor
+        const size_t row_pitch = size_t(p.ldc) * esz;
+        unsigned char* cst = p.c + (size_t(b) * p.c_batch + size_t(m0 + quad * 32 + rb) * p.ldc + n0) * esz + (q_st << 4);
+        const unsigned char* lds0 = buf + rb * 128;              // + it * 512; chunk (q_st ^ (r & 7)) with r & 7 = (rb + 4 it) & 7
+        unsigned char* myrow = buf + lane * 128;
+        const int n_b = ncols * esz;                             // bytes of a tile row inside the tensor
+        for (int c0 = half * ce; c0 < ncols; c0 += 2 * ce) {
+            const bool cols_in = n0 + c0 + ce <= n_valid;        // no column of this chunk is past the batch entry's n_len
+#pragma unroll
+            for (int h = 0; h < (CT == 0 ? 1 : 2); ++h) {
                 float v[32];
                 tc::tmem_ld32(tlane + uint32_t(c0 + 32 * h), v);
-                const int jbase = n0 + c0 + 32 * h;
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
                     float x = v[k] * p.alpha;
-                    if (p.act == 1) x = fmaxf(x, 0.0f);
-                    else if (p.act == 2) x = gelu_erf(x);
-                    v[k] = (row_ok && jbase + k < n_valid) ? x : 0.0f;
+                    if (ACT == 1) x = fmaxf(x, 0.0f);
+                    if (ACT == 2) x = gelu_erf(x);
+                    v[k] = x;
                 }
-                if (p.c_bf16) {
+                if (!(row_ok && cols_in)) {                      // ragged edge: the rare path carries the masks
+                    const int jbase = n0 + c0 + 32 * h;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint4 w = p.c_f16
-                            ? make_uint4(pack_f16(v[8 * q], v[8 * q + 1]), pack_f16(v[8 * q + 2], v[8 * q + 3]),
-                                         pack_f16(v[8 * q + 4], v[8 * q + 5]), pack_f16(v[8 * q + 6], v[8 * q + 7]))
-                            : make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                                         pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-                        *reinterpret_cast<uint4*>(myrow + (((4 * h + q) ^ sw) << 4)) = w;
-                    }
-                } else {
+                    for (int k = 0; k < 32; ++k) v[k] = (row_ok && jbase + k < n_valid) ? v[k] : 0.0f;
+                }
+                if (CT == 0) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint4 w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
                                                    __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
                         *reinterpret_cast<uint4*>(myrow + ((q ^ sw) << 4)) = w;
                     }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 w = CT == 2
+                            ? make_uint4(pack_f16(v[8 * q], v[8 * q + 1]), pack_f16(v[8 * q + 2], v[8 * q + 3]),
+                                         pack_f16(v[8 * q + 4], v[8 * q + 5]), pack_f16(v[8 * q + 6], v[8 * q + 7]))
+                            : make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                                         pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+                        *reinterpret_cast<uint4*>(myrow + (((4 * h + q) ^ sw) << 4)) = w;
+                    }
                 }
             }
             __syncwarp();
             if (p.col_stats) {
                 // column sums over this warp's 32 rows (masked rows hold zeros): lane L takes the 32-bit word L of every
-                // staged row -- one fp32 column, or two bf16 columns (the values the next layer will read)
+                // staged row -- one fp32 column, or two 16-bit columns (the values the next layer will read)
                 float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
                 const int chunk = lane >> 2, within = (lane & 3) << 2;
 #pragma unroll 8
                 for (int r = 0; r < 32; ++r) {
                     const uint32_t w = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
-                    if (p.c_bf16) {
-                        const float a = p.c_f16 ? f16_lo(w) : __uint_as_float(w << 16);
-                        const float c = p.c_f16 ? f16_hi(w) : __uint_as_float(w & 0xffff0000u);
+                    if (CT != 0) {
+                        const float a = CT == 2 ? f16_lo(w) : __uint_as_float(w << 16);
+                        const float c = CT == 2 ? f16_hi(w) : __uint_as_float(w & 0xffff0000u);
                         s0 += a; q0 += a * a; s1 += c; q1 += c * c;
                     } else {
                         const float a = __uint_as_float(w);
@@ -268,7 +291,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     }
                 }
                 float* st = p.col_stats + (size_t(b) * p.parts + size_t(blockIdx.y) * 4 + quad) * size_t(p.N) * 2;
-                if (p.c_bf16) {
+                if (CT != 0) {
                     const int col = n0 + c0 + 2 * lane;
                     if (col < p.N) *reinterpret_cast<float2*>(st + size_t(col) * 2) = make_float2(s0, q0);
                     if (col + 1 < p.N) *reinterpret_cast<float2*>(st + size_t(col + 1) * 2) = make_float2(s1, q1);
@@ -277,15 +300,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     if (col < p.N) *reinterpret_cast<float2*>(st + size_t(col) * 2) = make_float2(s0, q0);
                 }
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                tc::tma_store_3d(&tmap_c, buf, n0 + c0, m0 + quad * 32, b);
-                tc::bulk_commit();
+            // coalesced stores: 8 lanes cover one staged row (128 B), a warp instruction four rows
+            unsigned char* dst0 = cst + size_t(c0) * esz;
+            const int col_b = c0 * esz + (q_st << 4);                          // byte offset of this lane's 16 B inside the tile row
+            if (rows_here == 32 && c0 * esz + 128 <= n_b) {                    // the whole chunk is inside the tensor
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(lds0 + it * 512 + ((q_st ^ ((rb + 4 * it) & 7)) << 4));
+                    *reinterpret_cast<uint4*>(dst0 + size_t(4 * it) * row_pitch) = w;
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = rb + 4 * it;
+                    if (r < rows_here && col_b < n_b) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(lds0 + it * 512 + ((q_st ^ (r & 7)) << 4));
+                        unsigned char* dst = dst0 + size_t(4 * it) * row_pitch;
+                        if (col_b + 16 <= n_b) {
+                            *reinterpret_cast<uint4*>(dst) = w;
+                        } else {                                               // N * esz is not a multiple of 16 B: the last few elements
+                            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                            for (int e2 = 0; e2 < (n_b - col_b) >> 1; ++e2)
+                                reinterpret_cast<uint16_t*>(dst)[e2] = uint16_t(ws[e2 >> 1] >> ((e2 & 1) * 16));
+                        }
+                    }
+                }
             }
+            __syncwarp();
         }
-        if (lane == 0) tc::bulk_wait_read<0>();
-        __syncwarp();
+        if (tr && threadIdx.x == 64) tr[6] = clock64();          // first epilogue warp done
     }
 
     tc::fence_before();
@@ -294,6 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tc::fence_after();
         tc::tmem_dealloc(tmem_base, uint32_t(p.tmem_cols));
     }
+    if (tr && threadIdx.x == 32) tr[7] = clock64();
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -335,6 +379,33 @@ int make_map3(CUtensorMap* map, const void* ptr, int dtype, long long inner, lon
     return 0;
 }
 
+template <bool TF32, int ACT, int CT>
+cudaError_t launch_one(dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<TF32, ACT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    gemm_kernel<TF32, ACT, CT><<<grid, kGThreads, smem, stream>>>(ma, mb, p);
+    return cudaSuccess;
+}
+
+template <bool TF32, int ACT>
+cudaError_t launch_ct(int ct, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+    if (ct == 0) return launch_one<TF32, ACT, 0>(grid, smem, stream, ma, mb, p);
+    if (ct == 1) return launch_one<TF32, ACT, 1>(grid, smem, stream, ma, mb, p);
+    return launch_one<TF32, ACT, 2>(grid, smem, stream, ma, mb, p);
+}
+
+cudaError_t launch_gemm(bool tf32, int act, int ct, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb,
+                        const GemmParams& p) {
+    if (tf32) {
+        if (act == 0) return launch_ct<true, 0>(ct, grid, smem, stream, ma, mb, p);
+        if (act == 1) return launch_ct<true, 1>(ct, grid, smem, stream, ma, mb, p);
+        return launch_ct<true, 2>(ct, grid, smem, stream, ma, mb, p);
+    }
+    if (act == 0) return launch_ct<false, 0>(ct, grid, smem, stream, ma, mb, p);
+    if (act == 1) return launch_ct<false, 1>(ct, grid, smem, stream, ma, mb, p);
+    return launch_ct<false, 2>(ct, grid, smem, stream, ma, mb, p);
+}
+
 }  // namespace
 
 int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
@@ -360,12 +431,12 @@ int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
     p.m_len = d->m_len; p.n_len = d->n_len; p.k_len = d->k_len;
     p.c = static_cast<unsigned char*>(d->c);
     p.col_stats = d->col_stats;
+    p.trace = static_cast<long long*>(d->trace);
     p.ldc = d->ldc; p.c_batch = d->c_batch;
     p.batch = d->batch; p.M = d->M; p.N = d->N; p.K = d->K;
     // Tile width: as few column tiles as 256 TMEM columns allow, each as narrow as N permits (UMMA N is any multiple of 16),
     // so that N = 160, 200 or 384 waste nothing; an MN-major B arrives in 128 B-wide boxes, hence multiples of 64 / 32.
-    // and the epilogue stores whole 128 B-wide chunks (32 fp32 / 64 two-byte columns), which must not reach into the next tile
-    const int n_unit = std::max(d->b_mn_major ? 128 / elem : 16, 128 / esz_c);
+    const int n_unit = d->b_mn_major ? 128 / elem : 16;
     int bn = d->bn;
     if (bn == 0) {
         const int nt = (d->N + 255) / 256;
@@ -402,7 +473,7 @@ int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
               (uint32_t(bn >> 3) << 17) | (uint32_t(kGM >> 4) << 24);
 
     const int me = 128 / elem;          // 64 bf16 / 32 fp32 indices per 128 B
-    CUtensorMap ma, mb, mc;
+    CUtensorMap ma, mb;
     int rc;
     if (!p.a_mn) rc = make_map3(&ma, d->a, d->dtype_ab, d->K, d->M, p.a_shared ? 1 : d->batch, d->lda, d->a_batch, p.kb, kGM, "A");
     else         rc = make_map3(&ma, d->a, d->dtype_ab, d->M, d->K, p.a_shared ? 1 : d->batch, d->lda, d->a_batch, me, p.kb, "A", elem == 4);
@@ -412,21 +483,12 @@ int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
     if (!p.b_mn) rc = make_map3(&mb, d->b, d->dtype_ab, d->K, d->N, b_third, d->ldb, b_third_stride, p.kb, bn, "B");
     else         rc = make_map3(&mb, d->b, d->dtype_ab, d->N, d->K, b_third, d->ldb, b_third_stride, me, p.kb, "B", elem == 4);
     if (rc) return rc;
-    rc = make_map3(&mc, d->c, d->dtype_c, d->N, d->M, d->batch, d->ldc, d->c_batch, p.c_bf16 ? 64 : 32, 32, "C");
-    if (rc) return rc;
 
     const size_t smem = size_t(p.stages) * (kStageA + size_t(bn) * 128) + sizeof(uint64_t) * (2 * kMaxStages + 2) + 1024;
     const dim3 grid((d->N + bn - 1) / bn, m_tiles, d->batch);
-    cudaError_t e;
-    if (d->dtype_ab == ISP_DTYPE_F32) {
-        e = cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_kernel<tf32>)");
-        gemm_kernel<true><<<grid, kGThreads, smem, stream>>>(ma, mb, mc, p);
-    } else {
-        e = cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_kernel<bf16>)");
-        gemm_kernel<false><<<grid, kGThreads, smem, stream>>>(ma, mb, mc, p);
-    }
+    cudaError_t e = launch_gemm(d->dtype_ab == ISP_DTYPE_F32, d->act, d->dtype_c == ISP_DTYPE_F32 ? 0 : (d->dtype_c == ISP_DTYPE_BF16 ? 1 : 2),
+                                grid, smem, stream, ma, mb, p);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_kernel)");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "gemm_kernel launch");
     return 0;

@@ -66,7 +66,8 @@ def _launch(desc: "_lib.GemmDesc", dev):
 
 
 def bgemm(x: torch.Tensor, y: torch.Tensor, *, out_dtype: torch.dtype = torch.float32, alpha: float = 1.0,
-          m_len=None, n_len=None, k_len=None, act=None, col_stats: bool = False, bn: int = 0, out: torch.Tensor | None = None):
+          m_len=None, n_len=None, k_len=None, act=None, col_stats: bool = False, bn: int = 0, out: torch.Tensor | None = None,
+          trace: torch.Tensor | None = None):
     """act(alpha * x @ y): x (batch, M, K), y (batch, K, N) -> (batch, M, N) in `out_dtype` (fp32 accumulate).
 
     m_len / n_len / k_len: optional (batch,) lengths; rows / columns of the result past them are zeros and the contraction
@@ -105,6 +106,7 @@ def bgemm(x: torch.Tensor, y: torch.Tensor, *, out_dtype: torch.dtype = torch.fl
     d.a_mn_major, d.b_mn_major = a_mn, b_mn
     d.taps, d.tap_shift, d.act, d.bn, d.skip_padding = 1, 0, ACT[act], bn, 0
     d.alpha = float(alpha)
+    d.trace = trace.data_ptr() if trace is not None else None
     _launch(d, dev)
     res = buf if out is not None else (buf[:, :, :N] if ldc != N else buf)
     return (res, stats) if col_stats else res
