@@ -20,8 +20,9 @@
  *   - return value: 0 = enqueued; < 0 = ISP_ERR_* (bad argument / unsupported
  *     shape / workspace too small); > 0 = a cudaError_t.  isp_last_error()
  *     returns a thread-local message for the last non-zero return;
- *   - re-entrant; the only process-wide state is a per-device one-time
- *     cudaFuncSetAttribute.
+ *   - re-entrant, PROVIDED nobody calls isp_set_option concurrently: the tuning knobs
+ *     behind it are unsynchronised process-wide globals meant for benchmarks and tests;
+ *     the only other process-wide state is a per-device cudaFuncSetAttribute.
  * There is no CPU fallback anywhere behind this ABI.
  */
 #ifndef ISP_TTS_B200_H
@@ -225,6 +226,7 @@ typedef struct isp_gemm_desc {
     int32_t dtype_ab, dtype_c, a_mn_major, b_mn_major;
     int32_t taps, tap_shift, act, bn, skip_padding;
     float alpha;
+    int32_t stages;   /* tuning: depth of the operand ring (2..6), 0 = chosen from the shape */
     void* trace;      /* debug only, normally NULL: device int64 (CTAs, 8), SM-clock stamps of each CTA's phases (tools/gemm_trace.py) */
 } isp_gemm_desc;
 int    isp_gemm_batched(const isp_gemm_desc* desc, void* stream);
@@ -236,11 +238,12 @@ int    isp_gemm_batched(const isp_gemm_desc* desc, void* stream);
  * isp_instance_norm_apply: masked instance norm (tts/modules/normalization.py:186-206) of a channels-last activation
  *   y (B, T, C; row stride ld_in) from the column statistics isp_gemm_batched left in `stats` (B, parts, C, 2):
  *   mean = sum / len, var = sumsq / len - mean^2 (biased), out = ((y - mean) / sqrt(var + eps) * weight + bias) for
- *   t < len[b], 0 past it.  weight / bias (C) fp32 or NULL.  In place (out == y) is allowed. */
+ *   t < len[b], 0 past it.  weight / bias (C) fp32 or NULL.  ws: B * C * 8 bytes, 8 B aligned (the per-channel scale and shift).
+ *   In place (out == y) is allowed; rows past len[b] are then left as they are (the GEMM wrote zeros there). */
 int    isp_prep_channels_last(const void* x, int in_dtype, int channels_first, const int64_t* len, void* out, int out_dtype,
                               int B, int C, int T, int Cp, void* stream);
 int    isp_instance_norm_apply(const void* y, int dtype, const float* stats, int parts, const float* weight, const float* bias,
-                               const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, void* stream);
+                               const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, void* ws, void* stream);
 
 /* Tuning knobs for benchmarks/tests (process-wide, not part of the drop-in contract).
  *   "mas.ring_rows"      rows of logits kept in flight per strip of 128 tokens, 0 = heuristic

@@ -34,7 +34,7 @@ class GemmDesc(ctypes.Structure):
                 ("batch", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
                 ("dtype_ab", ctypes.c_int32), ("dtype_c", ctypes.c_int32), ("a_mn_major", ctypes.c_int32), ("b_mn_major", ctypes.c_int32),
                 ("taps", ctypes.c_int32), ("tap_shift", ctypes.c_int32), ("act", ctypes.c_int32), ("bn", ctypes.c_int32),
-                ("skip_padding", ctypes.c_int32), ("alpha", ctypes.c_float), ("trace", ctypes.c_void_p)]
+                ("skip_padding", ctypes.c_int32), ("alpha", ctypes.c_float), ("stages", ctypes.c_int32), ("trace", ctypes.c_void_p)]
 
 
 class IspError(RuntimeError):
@@ -95,7 +95,7 @@ def load():
     lib.isp_soft_average_backward.restype = c_int
     lib.isp_prep_channels_last.argtypes = [vp, c_int, c_int, vp, vp, c_int, c_int, c_int, c_int, c_int, vp]
     lib.isp_prep_channels_last.restype = c_int
-    lib.isp_instance_norm_apply.argtypes = [vp, c_int, vp, c_int, vp, vp, vp, vp, c_int, c_int, c_int, c_i64, c_i64, f32, vp]
+    lib.isp_instance_norm_apply.argtypes = [vp, c_int, vp, c_int, vp, vp, vp, vp, c_int, c_int, c_int, c_i64, c_i64, f32, vp, vp]
     lib.isp_instance_norm_apply.restype = c_int
     lib.isp_gemm_batched.argtypes = [ctypes.POINTER(GemmDesc), vp]
     lib.isp_gemm_batched.restype = c_int

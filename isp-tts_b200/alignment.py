@@ -197,10 +197,20 @@ def stage_operands(q_host: Tensor, k_host: Tensor, text_len: Tensor, mel_len: Te
         raise ValueError("q_host and k_host must be contiguous")
     B, T1, D = q_host.shape
     T2 = k_host.shape[1]
+    if k_host.shape[0] != B or k_host.shape[2] != D:
+        raise ValueError(f"shape mismatch: q_host {tuple(q_host.shape)} vs k_host {tuple(k_host.shape)}")
+    # the kernel reads the lengths as int64 on the device: coerce like _loglik_cuda does (an int32 tensor would be misread)
+    text_len = text_len.to(device=dev, dtype=torch.int64).contiguous()
+    mel_len = mel_len.to(device=dev, dtype=torch.int64).contiguous()
+    if text_len.numel() != B or mel_len.numel() != B:
+        raise ValueError("text_len and mel_len must hold one length per utterance")
     if out_q is None:
         out_q = torch.empty((B, T1, D), dtype=q_host.dtype, device=dev)
     if out_k is None:
         out_k = torch.empty((B, T2, D), dtype=k_host.dtype, device=dev)
+    for name, t, shape in (("out_q", out_q, (B, T1, D)), ("out_k", out_k, (B, T2, D))):
+        if tuple(t.shape) != shape or t.dtype != q_host.dtype or t.device != dev or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous {q_host.dtype} tensor of shape {shape} on {dev}")
     dt = _lib.ISP_DTYPE_BF16 if q_host.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
     with torch.cuda.device(dev):
         rc = lib.isp_stage_operands(q_host.data_ptr(), k_host.data_ptr(), dt, text_len.data_ptr(), mel_len.data_ptr(),

@@ -159,8 +159,8 @@ int isp_prep_channels_last(const void* x, int in_dtype, int channels_first, cons
 }
 
 int isp_instance_norm_apply(const void* y, int dtype, const float* stats, int parts, const float* weight, const float* bias,
-                            const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, void* stream) {
-    return isp::instance_norm_apply(y, dtype, stats, parts, weight, bias, len, out, B, T, C, ld_in, ld_out, eps, static_cast<cudaStream_t>(stream));
+                            const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, void* ws, void* stream) {
+    return isp::instance_norm_apply(y, dtype, stats, parts, weight, bias, len, out, B, T, C, ld_in, ld_out, eps, ws, static_cast<cudaStream_t>(stream));
 }
 
 int isp_gemm_batched(const isp_gemm_desc* desc, void* stream) { return isp::gemm_batched(desc, static_cast<cudaStream_t>(stream)); }

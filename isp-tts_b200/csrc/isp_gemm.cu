@@ -446,14 +446,12 @@ int gemm_batched(const isp_gemm_desc* d, cudaStream_t stream) {
     p.BN = bn;
     p.tmem_cols = 32;
     while (p.tmem_cols < bn) p.tmem_cols <<= 1;
-    // Ring depth: no deeper than the longest contraction needs (short ones then leave room for three or four CTAs per SM,
-    // which is what hides the per-tile latencies of a memory-bound GEMM), at most four, and at least the 32 KB of staging
-    const int kiters_max = taps * ((d->K + 128 / elem - 1) / (128 / elem));
-    p.stages = std::max(2, std::min(4, kiters_max));
-    // keep two CTAs on an SM (<= 108 KB each) unless the tile is the wide, long, compute-bound one: the epilogue of one then
-    // runs under the loads and MMAs of the other
-    const bool heavy = bn == 256 && kiters_max >= 16;
-    while (!heavy && p.stages > 2 && size_t(p.stages) * (kStageA + size_t(bn) * 128) > 108 * 1024) --p.stages;
+    // Ring depth: two stages.  What pays on every shape measured (tools/conv_bench.py, tools/gemm_bench.py) is more CTAs per SM,
+    // not a deeper ring per CTA: each CTA runs load -> MMA -> epilogue in sequence, so the overlap of one tile's epilogue with
+    // another's loads and MMAs comes from co-resident CTAs (key convolution, 128 x 256 tiles, K = 1920: 178 us with four stages and
+    // one CTA per SM, 142 us with two stages and two CTAs).
+    p.stages = 2;
+    if (d->stages >= 2 && d->stages <= kMaxStages) p.stages = d->stages;      // tuning override
     p.kb = 128 / elem;
     p.kblocks = (d->K + p.kb - 1) / p.kb;
     p.taps = taps; p.tap_shift = d->tap_shift;

@@ -60,7 +60,7 @@ int    soft_average_backward(const float* g, const float* x, const float* out, c
 int    prep_channels_last(const void* x, int in_dtype, int channels_first, const int64_t* len, void* out, int out_dtype,
                           int B, int C, int T, int Cp, cudaStream_t stream);
 int    instance_norm_apply(const void* y, int dtype, const float* stats, int parts, const float* weight, const float* bias,
-                           const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, cudaStream_t stream);
+                           const int64_t* len, void* out, int B, int T, int C, int64_t ld_in, int64_t ld_out, float eps, void* ws, cudaStream_t stream);
 int    gemm_batched(const isp_gemm_desc* d, cudaStream_t stream);
 int    stage_set_option(const char* key, int value, int* prev);
 

@@ -113,10 +113,11 @@ def bgemm(x: torch.Tensor, y: torch.Tensor, *, out_dtype: torch.dtype = torch.fl
 
 
 def conv1d_channels_last(x: torch.Tensor, w_taps: torch.Tensor, lengths=None, *, act=None, out_dtype: torch.dtype = torch.bfloat16,
-                         col_stats: bool = False, bn: int = 0):
+                         col_stats: bool = False, bn: int = 0, stages: int = 0):
     """'same' Conv1d without bias on a channels-last activation, as an implicit GEMM (alignment.py:58-62):
     x (B, T, Cin), w_taps (k, Cout, Cin) = conv.weight.permute(2, 0, 1), rows of x past `lengths` must be zero ->
-    act(conv) (B, T, Cout), rows past `lengths` zero; with col_stats the masked column sums for the instance norm."""
+    act(conv) (B, T, Cout), rows past `lengths` zero; with col_stats the masked column sums for the instance norm (slabs of
+    128-row tiles that lie wholly past `lengths` are left undefined: isp_instance_norm_apply does not read them)."""
     dev = x.device
     _lib.require_device(dev)
     if x.dtype != w_taps.dtype:
@@ -136,7 +137,8 @@ def conv1d_channels_last(x: torch.Tensor, w_taps: torch.Tensor, lengths=None, *,
     esz_c = 4 if out_dtype == torch.float32 else 2
     ldc = (Cout * esz_c + 15) // 16 * 16 // esz_c
     buf = torch.empty((B, T, ldc), dtype=out_dtype, device=dev)
-    stats = torch.zeros((B, 4 * ((T + 127) // 128), Cout, 2), dtype=torch.float32, device=dev) if col_stats else None
+    # not zeroed: only the slabs of tiles below ceil(len / 128) are written, and isp_instance_norm_apply reads exactly those
+    stats = torch.empty((B, 4 * ((T + 127) // 128), Cout, 2), dtype=torch.float32, device=dev) if col_stats else None
     lens, lens_ptr = _len_ptr(lengths, dev)
     d = _lib.GemmDesc()
     d.a, d.b, d.c = x.data_ptr(), w_taps.data_ptr(), buf.data_ptr()
@@ -150,6 +152,7 @@ def conv1d_channels_last(x: torch.Tensor, w_taps: torch.Tensor, lengths=None, *,
     d.a_mn_major, d.b_mn_major = 0, 0
     d.taps, d.tap_shift, d.act, d.bn, d.skip_padding = k, -(k // 2), ACT[act], bn, 0
     d.alpha = 1.0
+    d.stages = stages
     _launch(d, dev)
     res = buf[:, :, :Cout] if ldc != Cout else buf
     return (res, stats) if col_stats else res

@@ -92,10 +92,11 @@ def instance_norm_apply(y: torch.Tensor, stats: torch.Tensor, norm, lengths: tor
     w = norm.weight.detach().float().contiguous() if norm.weight is not None else None
     b = norm.bias.detach().float().contiguous() if norm.bias is not None else None
     dt = _lib.dtype_code(y.dtype)
+    ws = torch.empty((B, C, 2), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.isp_instance_norm_apply(y.data_ptr(), dt, stats.data_ptr(), stats.shape[1], w.data_ptr() if w is not None else None,
                                          b.data_ptr() if b is not None else None, lengths.data_ptr(), y.data_ptr(), B, T, C,
-                                         y.stride(1), y.stride(1), float(norm.eps), torch.cuda.current_stream(dev).cuda_stream)
+                                         y.stride(1), y.stride(1), float(norm.eps), ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "isp_instance_norm_apply")
     return y
 
