@@ -46,7 +46,8 @@ extern "C" {
 #define ISP_DTYPE_BF16 1          /* bf16 in memory, fp32 accumulate */
 #define ISP_DTYPE_F16  2          /* fp16 in memory, fp32 accumulate (isp_gemm_batched and its element-wise companions only) */
 
-#define ISP_MAS_MAX_T2   640      /* text tokens per utterance the MAS kernel covers */
+#define ISP_MAS_MAX_T2   640      /* text tokens per utterance the fast (strip) MAS kernels cover */
+#define ISP_MAS_WIDE_MAX_T2 16384 /* beyond ISP_MAS_MAX_T2 a general, slower kernel runs: up to this many tokens */
 #define ISP_LOGLIK_MAX_T2 512     /* text tokens per utterance the fused GEMM covers (TMEM columns) */
 #define ISP_LOGLIK_MAX_D  256     /* attention_dim */
 
@@ -76,7 +77,8 @@ int         isp_device_check(void);
  * ws        isp_mas_workspace_bytes(B,T1max,T2max) bytes, 16 B aligned; holds the status word,
  *           the packed backpointer bits when they do not fit in shared memory, and the
  *           path's column per frame until the zero-fill of attn_hard has landed.
- * Limits:   T2max <= ISP_MAS_MAX_T2; T1max < 2^24.
+ * Limits:   T2max <= ISP_MAS_WIDE_MAX_T2 (above ISP_MAS_MAX_T2 = 640 tokens a general kernel runs: one barrier per frame
+ *           row instead of the strip wavefront, same results); T1max < 2^24.
  * Results are bit-identical to the reference for NaN-free input.
  */
 size_t isp_mas_workspace_bytes(int B, int T1max, int T2max);

@@ -27,6 +27,11 @@ int    mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* t
                     int B, int T1max, int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws,
                     int no_tma, int ring_rows, int slots, int dbg, cudaStream_t stream);
 int    mas2_set_option(const char* key, int value, int* prev);
+// general kernel for wide utterances (isp_mas_wide.cu): any T2max <= ISP_MAS_WIDE_MAX_T2
+bool   mas_wide_supported(int T2max);
+size_t mas_wide_workspace_bytes(int B, int T1max, int T2max);
+int    mas_wide_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text_len, const int64_t* mel_len, int B, int T1max,
+                        int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, cudaStream_t stream);
 
 size_t loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,

@@ -57,6 +57,7 @@
 // Bit-exactness: each cell does exactly the reference's one fp32 add on top of an exact
 // max; the comparison is the reference's `>=` (ties and -inf >= -inf take the diagonal).
 
+#include <algorithm>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -724,7 +725,7 @@ static int g_opt_dbg = 0;
 static int g_opt_bits_global = 0;
 static int g_opt_no_tma = 0;
 static int g_opt_cols = 0;     // accepted for compatibility with older tools; the kernel has one strip width
-static int g_opt_impl = 0;     // 0: isp_mas2.cu where it covers the shape, 1: always this file's kernel, 2: isp_mas2.cu or fail
+static int g_opt_impl = 0;     // 0: isp_mas2.cu where it covers the shape, 1: always this file's kernel, 2: isp_mas2.cu or fail, 3: isp_mas_wide.cu
 
 int mas_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas.ring_rows")) { *prev = g_opt_ring_rows; g_opt_ring_rows = value; return 0; }
@@ -847,10 +848,12 @@ static bool make_maps(MasMaps* maps, const float* logp, int64_t sB, int64_t sT1,
 
 size_t mas_workspace_bytes(int B, int T1max, int T2max) {
     if (B <= 0 || T1max <= 0 || T2max <= 0) return 0;
+    if (T2max > ISP_MAS_MAX_T2) return mas_wide_workspace_bytes(B, T1max, T2max);      // the general kernel (isp_mas_wide.cu)
     const int ns = (T2max + kW - 1) / kW;
     const size_t v1 = 256 + size_t(B) * bits_words_for(T1max, ns) * 4 + ((size_t(B) * T1max * 2 + 15) & ~size_t(15));
     const size_t v2 = mas2_workspace_bytes(B);
-    return v1 > v2 ? v1 : v2;
+    const size_t v3 = mas_wide_workspace_bytes(B, T1max, T2max);     // "mas.impl" = 3 runs the general kernel on any shape (tests)
+    return std::max(v1, std::max(v2, v3));
 }
 
 template <bool BS, bool MULTI>
@@ -874,14 +877,16 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
     if (B <= 0 || T1max <= 0 || T2max <= 0) { set_error("isp_mas_forward: B, T1max, T2max must be positive"); return ISP_ERR_INVALID; }
     if (sT2 != 1) { set_error("isp_mas_forward: sT2 must be 1 (token axis contiguous), got %lld", (long long)sT2); return ISP_ERR_INVALID; }
     if (sT1 < T2max || (B > 1 && sB < int64_t(T1max - 1) * sT1 + T2max)) { set_error("isp_mas_forward: overlapping strides"); return ISP_ERR_INVALID; }
-    if (T2max > ISP_MAS_MAX_T2 || T1max >= (1 << 24)) {
-        set_error("isp_mas_forward: T2max=%d > %d or T1max=%d >= 2^24 is not covered", T2max, ISP_MAS_MAX_T2, T1max);
+    if (T1max >= (1 << 24) || (T2max > ISP_MAS_MAX_T2 && !mas_wide_supported(T2max))) {
+        set_error("isp_mas_forward: T2max=%d > %d or T1max=%d >= 2^24 is not covered", T2max, ISP_MAS_WIDE_MAX_T2, T1max);
         return ISP_ERR_UNSUPPORTED;
     }
     if (ws_bytes < mas_workspace_bytes(B, T1max, T2max) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
         set_error("isp_mas_forward: workspace too small or not 16 B aligned (%zu < %zu)", ws_bytes, mas_workspace_bytes(B, T1max, T2max));
         return ISP_ERR_WORKSPACE;
     }
+    if (T2max > ISP_MAS_MAX_T2 || g_opt_impl == 3)       // wider than the strip kernels: the general kernel (or forced, for tests)
+        return mas_wide_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws, stream);
     const bool want2 = g_opt_impl != 1 && !g_opt_bits_global && g_opt_slots != 3;
     if (want2 && mas2_supported(B, T1max, T2max))
         return mas2_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws,

@@ -45,7 +45,8 @@ def _reset_options():
 MODES = {"auto": {}, "unpaced_pairs": {"mas2.pace": 0, "mas.slots": 2}, "no_tma": {"mas.no_tma": 1}, "one_slot": {"mas.slots": 1}, "two_slots": {"mas.slots": 2},
          "pairs_in_turn": {"mas.slots": 2, "mas2.min_pair_stages": 64}, "two_slots_no_tma": {"mas.slots": 2, "mas.no_tma": 1},
          "v1": {"mas.impl": 1}, "v1_three_slots": {"mas.impl": 1, "mas.slots": 3}, "v1_bits_global": {"mas.impl": 1, "mas.bits_global": 1},
-         "v1_two_slots_global_no_tma": {"mas.impl": 1, "mas.slots": 2, "mas.bits_global": 1, "mas.no_tma": 1}}
+         "v1_two_slots_global_no_tma": {"mas.impl": 1, "mas.slots": 2, "mas.bits_global": 1, "mas.no_tma": 1},
+         "wide": {"mas.impl": 3}}          # isp_mas_wide.cu, the general kernel behind T2max > 640, forced onto every shape
 
 
 def set_mode(mode):
@@ -151,8 +152,36 @@ def test_maximum_width(cuda_device):
     hard, dur, _ = run_cuda(x, tl, ml, cuda_device)       # text longer than mel: pure diagonal tail
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
     assert_same(hard, dur, rh, rd, "T2=640")
-    with pytest.raises(_lib.IspError):
-        mas_forward(torch.zeros(1, 4, 641, device=cuda_device), torch.tensor([641]), torch.tensor([4]))
+    # one token more: the general kernel (isp_mas_wide.cu) takes over, same answers
+    x = synth.noise_logits(2, 300, 641, 12, quantize=0.5)
+    tl, ml = np.array([641, 450]), np.array([300, 211])
+    hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, "T2=641")
+    with pytest.raises(_lib.IspError):                     # ISP_MAS_WIDE_MAX_T2
+        mas_forward(torch.zeros(1, 2, 16385, device=cuda_device), torch.tensor([16385]), torch.tensor([2]))
+
+
+@pytest.mark.parametrize("shape", [(3, 900, 1000), (2, 2500, 2100), (2, 700, 4097), (1, 5000, 1024)])
+def test_wide_utterances_general_kernel(cuda_device, shape):
+    """T2max > 640 (long-form text): isp_mas_wide.cu against the oracle, ragged, with ties, path and durations bit-exact,
+    also through the path-only entry point."""
+    B, T1, T2 = shape
+    x = synth.noise_logits(B, T1, T2, 77 + T2, quantize=0.25)
+    tl, ml = synth.lengths(B, T2, T1, True, 78 + T2)
+    tl[0], ml[0] = T2, T1
+    if B > 1:
+        tl[1], ml[1] = min(T2, 700), min(T1, 650)           # more tokens than frames: the pure diagonal
+    hard, dur, xt = run_cuda(x, tl, ml, cuda_device)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, f"wide {shape}")
+    assert np.array_equal(dur.sum(1), ml)
+    none, dur2, path = mas_forward(xt, torch.from_numpy(tl), torch.from_numpy(ml), return_path=True, dense=False)
+    assert none is None and np.array_equal(dur2.cpu().numpy(), rd)
+    ref_path = omas.path_from_hard(rh, ml)
+    got = path.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(got[b, :ml[b]], ref_path[b, :ml[b]]) and np.all(got[b, ml[b]:] == -1)
 
 
 def test_unaligned_and_strided_inputs(cuda_device):
