@@ -181,6 +181,13 @@ int    isp_loglik_forward(const void* Q, const void* K, int dtype,
                           float* attn_logits, float* attn_soft,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* The same epilogue for shapes isp_loglik_forward does not cover (T2max > ISP_LOGLIK_MAX_T2, attention_dim not a multiple of 8 or
+ * above ISP_LOGLIK_MAX_D): S (B, T1max, T2max; row stride ldS) are the UNscaled scores Q.K^T from isp_gemm_batched; the call
+ * does alignment.py:190-208 on them (scale, log_softmax over all T2max columns + log prior, masked softmax) one warp per frame
+ * row.  Slower than the fused kernel (the scores make a round trip through HBM), same results within the same tolerance. */
+int    isp_loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                       float scale, int attention_prior, float* attn_logits, float* attn_soft, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Backward of the log-likelihood, first stage: the gradient with respect to the scores S = Q.K^T.
  *

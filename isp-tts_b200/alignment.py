@@ -33,6 +33,8 @@ from .mas import mas_forward
 __all__ = ["stage_operands", "batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
            "Aligner", "AlignerConfig", "AlignerOutput", "loglik_forward"]
 
+_FUSED_MAX_T2, _FUSED_MAX_D = 512, 256      # ISP_LOGLIK_MAX_T2, ISP_LOGLIK_MAX_D of include/isp_tts_b200.h
+
 MISSING = "???"   # same sentinel string omegaconf uses; the reference's configs compare against it
 
 
@@ -171,6 +173,15 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
     ml = mel_len.to(device=dev, dtype=torch.int64).contiguous()
     logits = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
     soft = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
+    if T2 > _FUSED_MAX_T2 or D % 8 != 0 or D > _FUSED_MAX_D:
+        # outside the fused kernel's range (long-form text, odd attention_dim): scores from the batched GEMM, then the
+        # stand-alone row epilogue (isp_loglik_rows) -- slower by the scores' round trip through HBM, same results
+        s = bgemm(q, k.transpose(1, 2), m_len=ml, n_len=tl)
+        with torch.cuda.device(dev):
+            rc = lib.isp_loglik_rows(s.data_ptr(), s.stride(1), tl.data_ptr(), ml.data_ptr(), B, T1, T2, float(scale),
+                                     1 if prior else 0, logits.data_ptr(), soft.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "isp_loglik_rows")
+        return soft, logits
     dt = _lib.ISP_DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
     with torch.cuda.device(dev):
         rc = lib.isp_loglik_forward(q.data_ptr(), k.data_ptr(), dt, tl.data_ptr(), ml.data_ptr(), B, T1, T2, D,

@@ -99,6 +99,11 @@ int isp_loglik_forward(const void* Q, const void* K, int dtype, const int64_t* t
                                attn_logits, attn_soft, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int isp_loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                    float scale, int attention_prior, float* attn_logits, float* attn_soft, void* stream) {
+    return isp::loglik_rows(S, ldS, text_len, mel_len, B, T1max, T2max, scale, attention_prior, attn_logits, attn_soft, static_cast<cudaStream_t>(stream));
+}
+
 int isp_loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
                            int B, int T1max, int T2max, float scale, int attention_prior, void* dS, int ds_dtype, void* stream) {
     return isp::loglik_backward_ds(S, attn_soft, g_logits, g_soft, B, T1max, T2max, scale, attention_prior, dS, ds_dtype,

@@ -37,6 +37,8 @@ size_t loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
                       int B, int T1max, int T2max, int D, float scale, int attention_prior,
                       float* attn_logits, float* attn_soft, void* ws, size_t ws_bytes, cudaStream_t stream);
+int    loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
+                   float scale, int attention_prior, float* attn_logits, float* attn_soft, cudaStream_t stream);
 int    loglik_set_option(const char* key, int value, int* prev);
 int    loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
                           int B, int T1max, int T2max, float scale, int attention_prior, void* dS, int ds_dtype, cudaStream_t stream);

@@ -113,15 +113,38 @@ def test_without_prior(cuda_device):
     assert np.abs(logits - rl).max() < 2e-3 and np.abs(soft - rs).max() < 1e-3
 
 
-def test_unsupported_shapes_raise(cuda_device):
-    z = lambda *s: torch.zeros(*s, device=cuda_device)
+def test_unsupported_inputs_raise(cuda_device):
     one = torch.ones(1, dtype=torch.int64, device=cuda_device)
     with pytest.raises(_lib.IspError):
-        loglik_forward(z(1, 8, 12), z(1, 8, 12), one, one)            # D % 8 != 0
-    with pytest.raises(_lib.IspError):
-        loglik_forward(z(1, 8, 16), z(1, 513, 16), one, one)          # T2max > 512
-    with pytest.raises(_lib.IspError):
-        loglik_forward(torch.zeros(1, 8, 16), torch.zeros(1, 8, 16), one.cpu(), one.cpu())   # CPU tensors
+        loglik_forward(torch.zeros(1, 8, 16), torch.zeros(1, 8, 16), one.cpu(), one.cpu())   # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        loglik_forward(torch.zeros(1, 8, 16, device=cuda_device), torch.zeros(1, 8, 24, device=cuda_device), one, one)
+
+
+@pytest.mark.parametrize("shape,dtype", [((2, 300, 700, 64), "fp32"), ((2, 260, 1100, 128), "bf16"), ((3, 200, 48, 12), "fp32"),
+                                         ((2, 150, 64, 264), "bf16"), ((1, 130, 513, 80), "fp32")])
+def test_shapes_beyond_the_fused_kernel(cuda_device, shape, dtype):
+    """More than 512 tokens (long-form text), attention_dim that is not a multiple of 8 or exceeds 256: the batched GEMM plus
+    the stand-alone row epilogue (isp_loglik_rows) take over -- same tolerances as the fused kernel; MAS follows on the same
+    logits (its general kernel beyond 640 tokens), bit-exact against the oracle."""
+    from isp_tts_b200.mas import mas_forward
+    from oracle import mas as omas
+    B, T1, T2, D = shape
+    tl, ml = synth.lengths(B, T2, T1, True, 500 + T2)
+    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, 501 + T2)
+    if dtype == "bf16":
+        q = torch.from_numpy(q).to(torch.bfloat16).float().numpy()
+        k = torch.from_numpy(k).to(torch.bfloat16).float().numpy()
+    soft, logits = run(q, k, tl, ml, cuda_device, dtype)
+    rs, rl, parts = oll.loglik(q, k, tl, ml, return_parts=True)
+    tol = TOL["fp32"] if dtype == "fp32" else dict(rel=1e-3, abs=1e-4, soft=1e-3)
+    compare(soft, logits, rs, rl, oll.threshold_ambiguous(parts["prior_raw"]), tol, f"general path {shape} {dtype}")
+    hard, dur = mas_forward(torch.from_numpy(logits).to(cuda_device), torch.from_numpy(tl), torch.from_numpy(ml))
+    rh, rd = omas.b_mas_with_durations(logits, tl, ml)
+    assert np.array_equal(hard.cpu().numpy(), rh) and np.array_equal(dur.cpu().numpy(), rd)
+    s2, l2 = run(q, k, tl, ml, cuda_device, dtype, prior=False)
+    r2s, r2l = oll.loglik(q, k, tl, ml, attention_prior=False)
+    assert np.abs(l2 - r2l).max() < 5e-3 and np.abs(s2 - r2s).max() < 2e-3
 
 
 def test_backward_matches_torch_autograd(cuda_device):
