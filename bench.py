@@ -277,7 +277,7 @@ def run_ours(args, w):
     import torch.distributed as dist
 
     from isp_tts_b200 import synth
-    from isp_tts_b200.alignment import _loglik_cuda, stage_operands
+    from isp_tts_b200.alignment import _loglik_cuda, pack_rows, stage_operands, unpack_operands
     from isp_tts_b200.mas import mas_forward
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -339,6 +339,11 @@ def run_ours(args, w):
     copy_stream = torch.cuda.Stream(device=dev)
     bufs = [dict(q=torch.empty_like(q_dev), k=torch.empty_like(k_dev), tl=torch.empty_like(tl_dev), ml=torch.empty_like(ml_dev),
                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    if args.e2e_copy == "packed":
+        # the host holds the valid rows back to back (what a data loader that does not pad hands over): one plain DMA per tensor
+        qp_host, kp_host = pack_rows(q_host, ml).pin_memory(), pack_rows(k_host, tl).pin_memory()
+        for bf in bufs:
+            bf["qp"], bf["kp"] = torch.empty_like(qp_host, device=dev), torch.empty_like(kp_host, device=dev)
     dur_hosts = [torch.empty((B, T2), dtype=torch.int64).pin_memory() for _ in range(2)]
     hard_hosts = [torch.empty((B, T1, T2), dtype=torch.int16).pin_memory() for _ in range(2)] if args.e2e_outputs == "hard" else None
     state = {"i": 0}
@@ -349,7 +354,12 @@ def run_ours(args, w):
             copy_stream.wait_event(bf["free"])                 # the kernels that read this buffer two steps ago are done
             bf["tl"].copy_(tl_host, non_blocking=True)
             bf["ml"].copy_(ml_host, non_blocking=True)
-            if args.e2e_copy == "staged":
+            if args.e2e_copy == "packed":
+                # two copy-engine transfers of the packed rows, then a scatter into the padded operands on the device
+                bf["qp"].copy_(qp_host, non_blocking=True)
+                bf["kp"].copy_(kp_host, non_blocking=True)
+                unpack_operands(bf["qp"], bf["kp"], bf["tl"], bf["ml"], T1, T2, out_q=bf["q"], out_k=bf["k"])
+            elif args.e2e_copy == "staged":
                 # ragged staging: only the rows below the lengths cross PCIe, the padding is zero-filled on the device
                 stage_operands(q_host, k_host, bf["tl"], bf["ml"], out_q=bf["q"], out_k=bf["k"])
             else:
@@ -468,7 +478,7 @@ def run_ours(args, w):
     e2e_ms = max_over_ranks(s2.elapsed_time(e2))
     # The platform's ceiling for that leg: the same number of bytes per step as ONE plain pinned cudaMemcpyAsync on the copy
     # engine, all ranks at once, nothing else running (what the host side of the PCIe tree gives N GPUs together)
-    ceil_bytes = int((ml.sum() + tl.sum()) * D * q_host.element_size()) if args.e2e_copy == "staged" else \
+    ceil_bytes = int((ml.sum() + tl.sum()) * D * q_host.element_size()) if args.e2e_copy in ("staged", "packed") else \
         q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size()
     flat_host = q_host.view(-1)[: ceil_bytes // q_host.element_size()]
     flat_dev = torch.empty_like(flat_host, device=dev)
@@ -780,7 +790,7 @@ def run_ours(args, w):
 
     utts = global_B * args.steps
     valid_cells = float(global_cells if strong else (tl * ml).sum() * world) * args.steps
-    if args.e2e_copy == "staged":
+    if args.e2e_copy in ("staged", "packed"):
         h2d = int((ml.sum() + tl.sum()) * D * q_host.element_size()) + 16 * B
     else:
         h2d = q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size() + 16 * B
@@ -805,7 +815,9 @@ def run_ours(args, w):
                 "h2d_gbs_all_ranks": h2d * world / (e2e_ms / args.steps) / 1e6,
                 "link_ceiling_gbs": link_ceiling_gbs,
                 "link_ceiling": "aggregate H2D rate of plain pinned cudaMemcpyAsync of the same bytes on all ranks at once, nothing else running",
-                "api": ("isp_stage_operands (valid rows only over PCIe) + " if args.e2e_copy == "staged" else "")
+                "api": ({"staged": "isp_stage_operands (padded pinned host tensors; valid rows only cross PCIe, zero-copy reads) + ",
+                         "packed": "two cudaMemcpyAsync of PACKED pinned host buffers (valid rows back to back) + isp_unpack_operands + ",
+                         "padded": ""}[args.e2e_copy])
                        + "isp_loglik_forward + isp_mas_forward through isp_tts_b200.  In: pinned host Q, K (already cast to the GEMM's "
                        + ("bf16" if elem == 2 else "fp32") + " on the host, outside the timed region) and int64 lengths.  Out: the int64 durations"
                        + (" and the dense int16 attn_hard (the reference's CPU route hands back attn_hard, alignment.py:312)" if hard_hosts is not None
@@ -835,8 +847,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (cfg5 sweep: 64..4096 with the cfg3 length law); 0 = the workload's own")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="resident-input timing: replay the step as a CUDA graph (default) or launch it through the Python wrappers")
-    ap.add_argument("--e2e-copy", default="staged", choices=["staged", "padded"],
-                    help="end-to-end H2D of Q and K: isp_stage_operands (valid rows only) or plain copies of the padded tensors")
+    ap.add_argument("--e2e-copy", default="packed", choices=["packed", "staged", "padded"],
+                    help="end-to-end H2D of Q and K: packed rows by DMA + isp_unpack_operands (default), isp_stage_operands (zero-copy reads "
+                         "of the valid rows of padded host tensors), or plain copies of the padded tensors")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (sweeps)")
     ap.add_argument("--e2e-outputs", default="durations", choices=["durations", "hard"],
                     help="what the end-to-end leg reads back: the durations (default) or the durations and the dense attn_hard")

@@ -174,6 +174,14 @@ int    isp_mas_status(const void* ws, void* stream);
  * D * elem % 16 == 0, all tensors 16 B aligned. */
 int    isp_stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
                           int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* stream);
+/* The same operands arriving PACKED and already on the device: q_packed holds the valid rows of all utterances back to back
+ * (sum of mel_len rows of D elements; utterance b starts at the exclusive running sum of the lengths), k_packed likewise for
+ * text_len.  One plain cudaMemcpyAsync of each packed buffer from pinned host memory runs on a copy engine -- the transfer that
+ * scales when several GPUs share the host -- and this call scatters the rows into the padded (B, T, D) operands, padding rows
+ * zero-filled.  ws: isp_unpack_workspace_bytes(B) bytes, 8 B aligned. */
+size_t isp_unpack_workspace_bytes(int B);
+int    isp_unpack_operands(const void* q_packed, const void* k_packed, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                           int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* ws, size_t ws_bytes, void* stream);
 size_t isp_loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    isp_loglik_forward(const void* Q, const void* K, int dtype,
                           const int64_t* text_len, const int64_t* mel_len,

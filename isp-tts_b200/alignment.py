@@ -30,7 +30,7 @@ from . import _lib
 from .gemm import bgemm
 from .mas import mas_forward
 
-__all__ = ["stage_operands", "batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
+__all__ = ["stage_operands", "unpack_operands", "pack_rows", "batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
            "Aligner", "AlignerConfig", "AlignerOutput", "loglik_forward"]
 
 _FUSED_MAX_T2, _FUSED_MAX_D = 512, 256      # ISP_LOGLIK_MAX_T2, ISP_LOGLIK_MAX_D of include/isp_tts_b200.h
@@ -227,6 +227,46 @@ def stage_operands(q_host: Tensor, k_host: Tensor, text_len: Tensor, mel_len: Te
         rc = lib.isp_stage_operands(q_host.data_ptr(), k_host.data_ptr(), dt, text_len.data_ptr(), mel_len.data_ptr(),
                                     B, T1, T2, D, out_q.data_ptr(), out_k.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "isp_stage_operands")
+    return out_q, out_k
+
+
+def pack_rows(x: Tensor, lengths) -> Tensor:
+    """Host-side helper (tests, benchmarks, data loaders): the valid rows of a padded (B, T, D) tensor back to back,
+    (sum lengths, D) -- the packed form unpack_operands takes."""
+    return torch.cat([x[b, :int(n)] for b, n in enumerate(lengths)], dim=0).contiguous()
+
+
+def unpack_operands(q_packed: Tensor, k_packed: Tensor, text_len: Tensor, mel_len: Tensor, t1max: int, t2max: int,
+                    out_q: Tensor | None = None, out_k: Tensor | None = None):
+    """Packed operands ON THE DEVICE (valid rows back to back: (sum mel_len, D) and (sum text_len, D), e.g. the result of one
+    `packed_host.to(device, non_blocking=True)` per tensor -- a plain DMA) -> the padded q (B, t1max, D), k (B, t2max, D) that
+    loglik_forward loads, padding rows zero (isp_unpack_operands).  Enqueued on the current stream."""
+    dev = q_packed.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    if q_packed.dtype != k_packed.dtype or q_packed.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("q_packed and k_packed must both be float32 or both bfloat16")
+    if q_packed.dim() != 2 or k_packed.dim() != 2 or q_packed.shape[1] != k_packed.shape[1] or not q_packed.is_contiguous() or not k_packed.is_contiguous():
+        raise ValueError("q_packed (rows, D) and k_packed (rows, D) must be contiguous with the same D")
+    text_len = text_len.to(device=dev, dtype=torch.int64).contiguous()
+    mel_len = mel_len.to(device=dev, dtype=torch.int64).contiguous()
+    B, D = text_len.numel(), q_packed.shape[1]
+    if mel_len.numel() != B:
+        raise ValueError("text_len and mel_len must hold one length per utterance")
+    if out_q is None:
+        out_q = torch.empty((B, t1max, D), dtype=q_packed.dtype, device=dev)
+    if out_k is None:
+        out_k = torch.empty((B, t2max, D), dtype=k_packed.dtype, device=dev)
+    for name, t, shape in (("out_q", out_q, (B, t1max, D)), ("out_k", out_k, (B, t2max, D))):
+        if tuple(t.shape) != shape or t.dtype != q_packed.dtype or t.device != dev or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous {q_packed.dtype} tensor of shape {shape} on {dev}")
+    nb = lib.isp_unpack_workspace_bytes(B)
+    ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+    dt = _lib.ISP_DTYPE_BF16 if q_packed.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+    with torch.cuda.device(dev):
+        rc = lib.isp_unpack_operands(q_packed.data_ptr(), k_packed.data_ptr(), dt, text_len.data_ptr(), mel_len.data_ptr(), B, int(t1max),
+                                     int(t2max), D, out_q.data_ptr(), out_k.data_ptr(), ws.data_ptr(), nb, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "isp_unpack_operands")
     return out_q, out_k
 
 

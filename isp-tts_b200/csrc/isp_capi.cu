@@ -158,6 +158,13 @@ int isp_soft_average_backward(const float* g, const float* x, const float* out, 
     return isp::soft_average_backward(g, x, out, colsum, g_soft, B, C, T1max, T2max, static_cast<cudaStream_t>(stream));
 }
 
+size_t isp_unpack_workspace_bytes(int B) { return isp::unpack_workspace_bytes(B); }
+
+int isp_unpack_operands(const void* q_packed, const void* k_packed, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                        int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* ws, size_t ws_bytes, void* stream) {
+    return isp::unpack_operands(q_packed, k_packed, dtype, text_len, mel_len, B, T1max, T2max, D, q_dev, k_dev, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int isp_prep_channels_last(const void* x, int in_dtype, int channels_first, const int64_t* len, void* out, int out_dtype,
                            int B, int C, int T, int Cp, void* stream) {
     return isp::prep_channels_last(x, in_dtype, channels_first, len, out, out_dtype, B, C, T, Cp, static_cast<cudaStream_t>(stream));

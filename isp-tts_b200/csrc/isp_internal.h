@@ -53,6 +53,10 @@ int    temporal_average(const float* x, const int64_t* durations, float* out, in
 int    stage_operands(const void* q_host, const void* k_host, int dtype, const int64_t* text_len, const int64_t* mel_len,
                       int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, cudaStream_t stream);
 
+size_t unpack_workspace_bytes(int B);
+int    unpack_operands(const void* q_packed, const void* k_packed, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                       int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 size_t ctc_workspace_bytes(int B, int T1max, int T2max);
 int    ctc_forward(const float* logits, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                    float blank_logprob, float* nll, void* ws, size_t ws_bytes, cudaStream_t stream);

@@ -291,3 +291,21 @@ def test_full_size_cfg3_bf16_against_oracle(cuda_device):
 def test_full_size_cfg4_against_oracle(cuda_device):
     """BASELINE.json configs[3]: 512 tokens x 4096 frames, batch 16 (both TMEM accumulator chunks, 32 frame tiles per utterance)."""
     _full_size_against_oracle(cuda_device, "cfg4", "bf16", 1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B", [5, 1300])
+def test_unpack_operands_packed_upload(cuda_device, dtype, B):
+    """isp_unpack_operands: packed valid rows (one plain DMA each) -> padded operands, bit-exact rows, zero padding; the batch of
+    1300 exercises the chunked scan of the offsets."""
+    from isp_tts_b200.alignment import pack_rows, unpack_operands
+    T1, T2, D = (300, 70, 128) if B < 100 else (40, 12, 16)
+    tl, ml = synth.lengths(B, T2, T1, True, 91)
+    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, 92)
+    qh, kh = torch.from_numpy(q).to(dtype), torch.from_numpy(k).to(dtype)
+    qp, kp = pack_rows(qh, ml).pin_memory(), pack_rows(kh, tl).pin_memory()
+    assert qp.shape == (int(ml.sum()), D) and kp.shape == (int(tl.sum()), D)
+    qd, kd = unpack_operands(qp.to(cuda_device, non_blocking=True), kp.to(cuda_device, non_blocking=True),
+                             torch.from_numpy(tl), torch.from_numpy(ml), T1, T2)
+    torch.cuda.synchronize()
+    assert torch.equal(qd.cpu(), qh) and torch.equal(kd.cpu(), kh)          # synth's padding rows are zeros
