@@ -277,7 +277,7 @@ def run_ours(args, w):
     import torch.distributed as dist
 
     from isp_tts_b200 import synth
-    from isp_tts_b200.alignment import _loglik_cuda, pack_rows, stage_operands, unpack_operands
+    from isp_tts_b200.alignment import _align_cuda, _loglik_cuda, pack_rows, stage_operands, unpack_operands
     from isp_tts_b200.mas import mas_forward
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,6 +293,10 @@ def run_ours(args, w):
     if args.stage_ctas:
         from isp_tts_b200 import _lib as _l
         _l.set_option("stage.ctas", args.stage_ctas)
+    for kv in args.opt:
+        from isp_tts_b200 import _lib as _lo
+        key, val = kv.split("=")
+        _lo.set_option(key, int(val))
     if args.mas_ring or args.mas_slots:
         from isp_tts_b200 import _lib
         _lib.set_option("mas.ring_rows", args.mas_ring)
@@ -322,7 +326,12 @@ def run_ours(args, w):
     q_dev, k_dev = q_host.to(dev), k_host.to(dev)
     tl_dev, ml_dev = tl_host.to(dev), ml_host.to(dev)
 
+    linked = args.link == "on"
+
     def step_resident(events=None):
+        if linked and events is None:
+            # the product's step: isp_align_forward (both kernels, the second starting under the first's last wave)
+            return _align_cuda(q_dev, k_dev, tl_dev, ml_dev, scale, True)[3]
         if events is not None:
             events[0].record()
         soft, logits = _loglik_cuda(q_dev, k_dev, tl_dev, ml_dev, scale, True)
@@ -376,8 +385,11 @@ def run_ours(args, w):
         bf = bufs[slot]
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(bf["ready"])
-        soft, logits = _loglik_cuda(bf["q"], bf["k"], bf["tl"], bf["ml"], scale, True)
-        hard, dur = mas_forward(logits, bf["tl"], bf["ml"])
+        if linked:
+            soft, logits, hard, dur, _ = _align_cuda(bf["q"], bf["k"], bf["tl"], bf["ml"], scale, True)
+        else:
+            soft, logits = _loglik_cuda(bf["q"], bf["k"], bf["tl"], bf["ml"], scale, True)
+            hard, dur = mas_forward(logits, bf["tl"], bf["ml"])
         bf["free"].record(cur)
         dur_hosts[slot].copy_(dur, non_blocking=True)
         if hard_hosts is not None:
@@ -417,7 +429,14 @@ def run_ours(args, w):
     if launch == "graph":
         try:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # captured on a stream the step has already run on: the linked call keeps one workspace per stream and shape, and a
+            # workspace it has used before needs no memset in front of the kernels (ISP_ALIGN_WS_CLEAN)
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cap_stream):
+                step_resident()
+            cap_stream.synchronize()
+            with torch.cuda.graph(graph, stream=cap_stream):
                 dur_static = step_resident()
             for _ in range(3):
                 graph.replay()
@@ -446,7 +465,9 @@ def run_ours(args, w):
             t_step_g = st.elapsed_time(en) / max(10, min(args.steps, 50))
             if 0.0 < t_ll_g < t_step_g:
                 t_loglik, t_mas = t_ll_g, t_step_g - t_ll_g
-                kernel_timing = "graph replay: isp_loglik alone; isp_mas = step - isp_loglik (what it adds to the step, memset included)"
+                kernel_timing = ("graph replay: isp_loglik alone; isp_mas = step - isp_loglik (what it adds to the step)"
+                                 + ("; the step is isp_align_forward: the MAS kernel starts under the log-likelihood kernel's last wave, "
+                                    "launched on its own (isp_mas_forward) it takes ms_eager_events.isp_mas" if linked else ""))
         except Exception as exc:                                    # pragma: no cover
             print(f"[bench] per-kernel graph timing failed ({exc!r}); keeping the eager events", file=sys.stderr, flush=True)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -818,11 +839,12 @@ def run_ours(args, w):
                 "api": ({"staged": "isp_stage_operands (padded pinned host tensors; valid rows only cross PCIe, zero-copy reads) + ",
                          "packed": "two cudaMemcpyAsync of PACKED pinned host buffers (valid rows back to back) + isp_unpack_operands + ",
                          "padded": ""}[args.e2e_copy])
-                       + "isp_loglik_forward + isp_mas_forward through isp_tts_b200.  In: pinned host Q, K (already cast to the GEMM's "
+                       + ("isp_align_forward (the two kernels linked)" if linked else "isp_loglik_forward + isp_mas_forward") + " through isp_tts_b200.  In: pinned host Q, K (already cast to the GEMM's "
                        + ("bf16" if elem == 2 else "fp32") + " on the host, outside the timed region) and int64 lengths.  Out: the int64 durations"
                        + (" and the dense int16 attn_hard (the reference's CPU route hands back attn_hard, alignment.py:312)" if hard_hosts is not None
                           else " only; attn_hard, attn_logits and attn_soft stay on the device (--e2e-outputs hard also brings attn_hard back)")
                        + ".  The next step's H2D overlaps this step's kernels (two device buffers, one copy stream)"},
+        "step_api": "isp_align_forward" if linked else "isp_loglik_forward + isp_mas_forward",
         "next_rows": bwd, "durations_gather": gather,
         "gpu_launches": (2 + (1 if B > 512 else 0)) * args.steps,      # loglik + MAS (+ the MAS plan kernel beyond 512 utterances)
         "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
@@ -842,6 +864,10 @@ def main():
     ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--mas-ring", type=int, default=0, help="tuning: MAS logit rows in flight, 0 = heuristic")
     ap.add_argument("--mas-slots", type=int, default=0, help="tuning: utterances per CTA (1|2), 0 = heuristic")
+    ap.add_argument("--link", default="on", choices=["on", "off"],
+                    help="on: the step is isp_align_forward (log-likelihood and MAS kernels linked by per-utterance ready counts); "
+                         "off: isp_loglik_forward then isp_mas_forward")
+    ap.add_argument("--opt", action="append", default=[], help="tuning: isp_set_option key=value (repeatable), e.g. mas.pdl=0")
     ap.add_argument("--stage-ctas", type=int, default=0, help="tuning: CTAs of the host->device staging kernel, 0 = default")
     ap.add_argument("--no-backward", action="store_true", help="skip the f-1 backward measurement that follows the timed steps")
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (cfg5 sweep: 64..4096 with the cfg3 length law); 0 = the workload's own")

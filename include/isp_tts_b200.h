@@ -182,6 +182,27 @@ int    isp_stage_operands(const void* q_host, const void* k_host, int dtype, con
 size_t isp_unpack_workspace_bytes(int B);
 int    isp_unpack_operands(const void* q_packed, const void* k_packed, int dtype, const int64_t* text_len, const int64_t* mel_len,
                            int B, int T1max, int T2max, int D, void* q_dev, void* k_dev, void* ws, size_t ws_bytes, void* stream);
+/* The whole hot path in one call -- what Aligner.forward does between the projection stacks and its return
+ * (tts/models/acoustic/modules/alignment.py:253 self.attention(...), :267-275 binarize_attention + durations): the two kernels of
+ * isp_loglik_forward and isp_mas_forward[_path], linked so that the second does not wait for the first to drain.  The
+ * log-likelihood kernel counts, per utterance, the frame tiles whose outputs are in global memory (ws); the MAS kernel is
+ * launched with programmatic stream serialisation, becomes resident on the SMs the last wave of the first kernel leaves
+ * free, and each of its CTAs starts its utterance as soon as that utterance's count is final.  Arguments, outputs, limits and
+ * results are those of the two separate calls (bit-identical); shapes the linked kernels do not cover run as the plain
+ * sequence.  path may be NULL; attn_hard may be NULL when path is not.  ws: isp_align_workspace_bytes(...) bytes, 16 B aligned;
+ * isp_mas_status(ws, stream) works on it as after isp_mas_forward.  flags: 0, or ISP_ALIGN_WS_CLEAN when the last thing that
+ * touched ws was a successful isp_align_forward with the same B, T1max, T2max in the same stream (the call leaves its
+ * counters cleared, so the next one needs no memset in front of the kernels: one graph node and ~3 us less per step). */
+#define ISP_ALIGN_WS_CLEAN 1
+size_t isp_align_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
+int    isp_align_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                         int B, int T1max, int T2max, int D, float scale, int attention_prior,
+                         float* attn_logits, float* attn_soft, int16_t* attn_hard, int64_t* durations, int16_t* path,
+                         void* ws, size_t ws_bytes, int flags, void* stream);
+/* 1 when isp_loglik_forward (and isp_align_forward's linked kernels) cover the shape: D a multiple of 8 and <= ISP_LOGLIK_MAX_D,
+ * T2max <= ISP_LOGLIK_MAX_T2, and the operands of one frame tile plus one utterance's tokens fit in shared memory (fp32 operands
+ * with several hundred tokens at D = 128 do not).  Other shapes: isp_gemm_batched for the scores, then isp_loglik_rows. */
+int    isp_loglik_supported(int T2max, int D, int dtype);
 size_t isp_loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    isp_loglik_forward(const void* Q, const void* K, int dtype,
                           const int64_t* text_len, const int64_t* mel_len,

@@ -31,9 +31,8 @@ from .gemm import bgemm
 from .mas import mas_forward
 
 __all__ = ["stage_operands", "unpack_operands", "pack_rows", "batch_diagonal_prior", "ConvBlock1D", "ConvAttention", "ConvAttentionConfig",
-           "Aligner", "AlignerConfig", "AlignerOutput", "loglik_forward"]
+           "Aligner", "AlignerConfig", "AlignerOutput", "loglik_forward", "align_forward"]
 
-_FUSED_MAX_T2, _FUSED_MAX_D = 512, 256      # ISP_LOGLIK_MAX_T2, ISP_LOGLIK_MAX_D of include/isp_tts_b200.h
 
 MISSING = "???"   # same sentinel string omegaconf uses; the reference's configs compare against it
 
@@ -173,8 +172,9 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
     ml = mel_len.to(device=dev, dtype=torch.int64).contiguous()
     logits = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
     soft = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
-    if T2 > _FUSED_MAX_T2 or D % 8 != 0 or D > _FUSED_MAX_D:
-        # outside the fused kernel's range (long-form text, odd attention_dim): scores from the batched GEMM, then the
+    dt = _lib.ISP_DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+    if not lib.isp_loglik_supported(T2, D, dt):
+        # outside the fused kernel's range (long-form text, odd attention_dim, fp32 operands too wide for shared memory): scores from the batched GEMM, then the
         # stand-alone row epilogue (isp_loglik_rows) -- slower by the scores' round trip through HBM, same results
         s = bgemm(q, k.transpose(1, 2), m_len=ml, n_len=tl)
         with torch.cuda.device(dev):
@@ -182,13 +182,77 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
                                      1 if prior else 0, logits.data_ptr(), soft.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "isp_loglik_rows")
         return soft, logits
-    dt = _lib.ISP_DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
     with torch.cuda.device(dev):
         rc = lib.isp_loglik_forward(q.data_ptr(), k.data_ptr(), dt, tl.data_ptr(), ml.data_ptr(), B, T1, T2, D,
                                     float(scale), 1 if prior else 0, logits.data_ptr(), soft.data_ptr(), None, 0,
                                     torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "isp_loglik_forward")
     return soft, logits
+
+
+def _align_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool, return_path: bool = False,
+                dense: bool = True):
+    """isp_align_forward: the log-likelihood kernel and the MAS kernel linked through per-utterance ready counts (the second
+    starts under the first's last wave).  Returns (soft, logits, hard, durations, path)."""
+    dev = q.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    if q.dtype != k.dtype or q.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("Q and K must both be float32 or both bfloat16")
+    B, T1, D = q.shape
+    T2 = k.shape[1]
+    if k.shape[0] != B or k.shape[2] != D:
+        raise ValueError(f"shape mismatch: Q {tuple(q.shape)} vs K {tuple(k.shape)}")
+    if not dense and not return_path:
+        raise ValueError("dense=False needs return_path=True")
+    dt = _lib.ISP_DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+    if not lib.isp_loglik_supported(T2, D, dt):
+        soft, logits = _loglik_cuda(q, k, text_len, mel_len, scale, prior)
+        out = mas_forward(logits, text_len, mel_len, durations=True, return_path=return_path, dense=dense)
+        return soft, logits, out[0], out[1], (out[2] if return_path else None)
+    q = q.contiguous()
+    k = k.contiguous()
+    tl = text_len.to(device=dev, dtype=torch.int64).contiguous()
+    ml = mel_len.to(device=dev, dtype=torch.int64).contiguous()
+    if tl.numel() != B or ml.numel() != B:
+        raise ValueError("text_len / mel_len must have one entry per utterance")
+    logits = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
+    soft = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
+    hard = torch.empty((B, T1, T2), dtype=torch.int16, device=dev) if dense else None
+    dur = torch.empty((B, T2), dtype=torch.int64, device=dev)
+    path = torch.empty((B, T1), dtype=torch.int16, device=dev) if return_path else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws, clean = _align_workspace(lib, dev, stream, B, T1, T2, D, dt)
+        rc = lib.isp_align_forward(q.data_ptr(), k.data_ptr(), dt, tl.data_ptr(), ml.data_ptr(), B, T1, T2, D, float(scale),
+                                   1 if prior else 0, logits.data_ptr(), soft.data_ptr(), hard.data_ptr() if hard is not None else None,
+                                   dur.data_ptr(), path.data_ptr() if path is not None else None, ws.data_ptr(), ws.numel(),
+                                   _lib.ISP_ALIGN_WS_CLEAN if clean else 0, stream)
+    if rc != 0:
+        _ALIGN_WS.clear()
+    _lib.check(rc, "isp_align_forward")
+    return soft, logits, hard, dur, path
+
+
+# Workspaces of the linked call, one per (device, stream, shape): a workspace that only ever saw successful calls of one shape in
+# one stream is left clean by each of them (ISP_ALIGN_WS_CLEAN: no memset in front of the kernels).  9 MB at batch 256 x 1000 x 200
+# (isp_mas_workspace_bytes covers every MAS kernel); at most four are kept, none above 32 MB -- the linked kernels stop at 512
+# utterances anyway.
+_ALIGN_WS: dict = {}
+
+
+def _align_workspace(lib, dev, stream, B, T1, T2, D, dt):
+    key = (dev.index, int(stream), B, T1, T2)
+    ws = _ALIGN_WS.get(key)
+    if ws is not None:
+        return ws, True
+    nb = lib.isp_align_workspace_bytes(B, T1, T2, D, dt)
+    ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+    if nb <= (32 << 20) and not torch.cuda.is_current_stream_capturing():
+        if len(_ALIGN_WS) >= 4:
+            _ALIGN_WS.pop(next(iter(_ALIGN_WS)))
+        _ALIGN_WS[key] = ws
+    return ws, False
 
 
 def stage_operands(q_host: Tensor, k_host: Tensor, text_len: Tensor, mel_len: Tensor,
@@ -313,22 +377,37 @@ class _LogLikelihood(torch.autograd.Function):
     nothing is lost); every row of dQ / dK is computed, padded ones included, exactly as autograd would."""
 
     @staticmethod
-    def forward(ctx, q, k, text_len, mel_len, scale, prior):
+    def forward(ctx, q, k, text_len, mel_len, scale, prior, with_mas=False):
+        ctx.scale, ctx.prior, ctx.with_mas = scale, prior, with_mas
+        if with_mas:
+            # the linked call (isp_align_forward): the hard path and the durations come with it, outside autograd
+            soft, logits, hard, dur, _ = _align_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior)
+            ctx.save_for_backward(q, k, soft, text_len, mel_len)
+            ctx.mark_non_differentiable(hard, dur)
+            return soft, logits, hard, dur
         soft, logits = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior)
         ctx.save_for_backward(q, k, soft, text_len, mel_len)
-        ctx.scale, ctx.prior = scale, prior
         return soft, logits
 
     @staticmethod
-    def backward(ctx, g_soft, g_logits):
+    def backward(ctx, g_soft, g_logits, *_):
         q, k, soft, text_len, mel_len = ctx.saved_tensors
         if g_soft is None and g_logits is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         qd, kd = q.detach().contiguous(), k.detach().contiguous()
         d_s = loglik_backward_ds(_scores(qd, kd, text_len, mel_len), soft, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
         gq = bgemm(d_s, kd, out_dtype=q.dtype, k_len=text_len) if ctx.needs_input_grad[0] else None
         gk = bgemm(d_s.transpose(1, 2), qd, out_dtype=k.dtype, k_len=mel_len) if ctx.needs_input_grad[1] else None
-        return gq, gk, None, None, None, None
+        return gq, gk, None, None, None, None, None
+
+
+def align_forward(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float | None = None,
+                  attention_prior: bool = True):
+    """The whole hot path in one linked call (isp_align_forward): (attn_soft, attn_logits, attn_hard int16, durations int64)
+    from encoded frames q (B, T1, D) and tokens k (B, T2, D).  attn_soft and attn_logits carry gradients to q and k exactly as
+    loglik_forward's do; the hard path and the durations are outside autograd (alignment.py:291 torch.no_grad)."""
+    scale = q.shape[-1] ** -0.5 if scale is None else scale
+    return _LogLikelihood.apply(q, k, text_len, mel_len, scale, attention_prior, True)
 
 
 def loglik_forward(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float | None = None,
@@ -477,12 +556,20 @@ class ConvAttention(nn.Module, _ConfigInit):
     def forward(self, queries: Tensor, keys: Tensor, query_len: Tensor, key_len: Tensor):
         """queries (B, mel_dim, T1) mel, keys (B, text_dim, T2) encoded text, lengths (B,)
         -> (attn_soft, attn_logits), both (B, T1, T2) fp32 (alignment.py:159-208)."""
+        q, k = self._operands(queries, keys, query_len, key_len)
+        return loglik_forward(q, k, key_len, query_len, self.scale, self.attention_prior)
+
+    def _operands(self, queries: Tensor, keys: Tensor, query_len: Tensor, key_len: Tensor):
         q, k = self.encode(queries, keys, query_len, key_len)
         if self._mode() == "bf16":
-            q, k = q.to(torch.bfloat16), k.to(torch.bfloat16)
-        else:
-            q, k = q.float(), k.float()
-        return loglik_forward(q, k, key_len, query_len, self.scale, self.attention_prior)
+            return q.to(torch.bfloat16), k.to(torch.bfloat16)
+        return q.float(), k.float()
+
+    def forward_aligned(self, queries: Tensor, keys: Tensor, query_len: Tensor, key_len: Tensor):
+        """forward() plus the MAS hard path and the durations from the same linked call (align_forward):
+        (attn_soft, attn_logits, attn_hard, durations)."""
+        q, k = self._operands(queries, keys, query_len, key_len)
+        return align_forward(q, k, key_len, query_len, self.scale, self.attention_prior)
 
 
 class AlignerOutput(NamedTuple):
@@ -503,8 +590,9 @@ class Aligner(nn.Module, _ConfigInit):
                                        attention_prior=attention_prior)
 
     def forward(self, mel: Tensor, enc_text: Tensor, mel_len: Tensor, text_len: Tensor) -> AlignerOutput:
-        attn_soft, attn_logits = self.attention(queries=mel, keys=enc_text, query_len=mel_len, key_len=text_len)
-        attn_hard, duration = self._align(attn_logits, text_len, mel_len)
+        # alignment.py:253 + :267-275 as one linked call: the MAS kernel starts under the log-likelihood kernel's last wave
+        attn_soft, attn_logits, attn_hard, duration = self.attention.forward_aligned(queries=mel, keys=enc_text, query_len=mel_len,
+                                                                                    key_len=text_len)
         # every valid frame gets exactly one 1, so durations sum to mel_len by construction and the
         # reference's print-and-patch check (alignment.py:278-282, a device->host sync) never fires
         return AlignerOutput(attn_soft=attn_soft, attn_logits=attn_logits, attn_hard=attn_hard,

@@ -88,6 +88,48 @@ int isp_mas_status(const void* ws, void* stream) {
     return bad;
 }
 
+static int g_align_mode = 0;     // experiments: 0 linked; 1 counts published, MAS launched plainly behind; 2 the plain sequence
+
+// workspace of isp_align_forward: the MAS workspace, then (256 B aligned) the per-utterance ready counts
+static size_t align_ready_offset(int B, int T1max, int T2max) { return (isp::mas_workspace_bytes(B, T1max, T2max) + 255) & ~size_t(255); }
+
+size_t isp_align_workspace_bytes(int B, int T1max, int T2max, int D, int dtype) {
+    (void)D; (void)dtype;
+    if (B <= 0 || T1max <= 0 || T2max <= 0) return 0;
+    return align_ready_offset(B, T1max, T2max) + ((size_t(B + 8) * sizeof(int) + 255) & ~size_t(255));       // + the launch's time origin
+}
+
+int isp_align_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
+                      int B, int T1max, int T2max, int D, float scale, int attention_prior,
+                      float* attn_logits, float* attn_soft, int16_t* attn_hard, int64_t* durations, int16_t* path,
+                      void* ws, size_t ws_bytes, int flags, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!ws || B <= 0 || T1max <= 0 || T2max <= 0) { isp::set_error("isp_align_forward: null workspace or non-positive sizes"); return ISP_ERR_INVALID; }
+    if (ws_bytes < isp_align_workspace_bytes(B, T1max, T2max, D, dtype) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+        isp::set_error("isp_align_forward: workspace too small or not 16 B aligned (%zu < %zu)", ws_bytes, isp_align_workspace_bytes(B, T1max, T2max, D, dtype));
+        return ISP_ERR_WORKSPACE;
+    }
+    const size_t off = align_ready_offset(B, T1max, T2max);
+    int* ready = reinterpret_cast<int*>(static_cast<char*>(ws) + off);
+    const bool link = g_align_mode != 2 && isp::mas_linkable(B, T1max, T2max);
+    const size_t ready_bytes = size_t(B + 8) * sizeof(int);      // counts, the MAS launch's time origin, two debug stamps
+    if (link && !(flags & ISP_ALIGN_WS_CLEAN)) {
+        // the counts are cleared in front of the first kernel, so that the second follows the first directly (a programmatic edge);
+        // a workspace that the previous successful call on it left behind is clean already (the MAS kernel resets what it consumed)
+        cudaError_t e = cudaMemsetAsync(ready, 0, ready_bytes, st);
+        if (e != cudaSuccess) return isp::cuda_fail(e, "cudaMemsetAsync(ready counts)");
+    }
+    int rc = isp::loglik_forward(Q, K, dtype, text_len, mel_len, B, T1max, T2max, D, scale, attention_prior, attn_logits, attn_soft,
+                                 nullptr, 0, st, link ? ready : nullptr);
+    if (rc) return rc;
+    rc = isp::mas_forward(attn_logits, int64_t(T1max) * T2max, T2max, 1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path,
+                          ws, off, st, link && g_align_mode == 0 ? ready : nullptr, isp::loglik_tiles_per_utterance(T1max));
+    if ((rc || g_align_mode == 1) && link) cudaMemsetAsync(ready, 0, ready_bytes, st);      // nobody consumed the counts: leave the workspace clean
+    return rc;
+}
+
+int isp_loglik_supported(int T2max, int D, int dtype) { return isp::loglik_supported(T2max, D, dtype) ? 1 : 0; }
+
 size_t isp_loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype) {
     return isp::loglik_workspace_bytes(B, T1max, T2max, D, dtype);
 }
@@ -180,6 +222,7 @@ int isp_gemm_batched(const isp_gemm_desc* desc, void* stream) { return isp::gemm
 int isp_set_option(const char* key, int value) {
     if (!key) return ISP_ERR_INVALID;
     int prev = 0;
+    if (!strcmp(key, "align.mode")) { prev = g_align_mode; g_align_mode = value; return prev; }
     if (isp::mas_set_option(key, value, &prev) == 0) return prev;
     if (isp::loglik_set_option(key, value, &prev) == 0) return prev;
     if (isp::stage_set_option(key, value, &prev) == 0) return prev;

@@ -16,16 +16,19 @@ int  cuda_fail(cudaError_t e, const char* what);
 size_t mas_workspace_bytes(int B, int T1max, int T2max);
 int    mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
                    const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
-                   int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, size_t ws_bytes, cudaStream_t stream);
+                   int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, size_t ws_bytes, cudaStream_t stream,
+                   const int* ready = nullptr, int ready_need = 0);
 int    bin_loss_sums(const float* attn_soft, const int16_t* path, const int64_t* mel_len, int B, int T1max, int T2max,
                      float eps, float* sums, cudaStream_t stream);
 int    mas_set_option(const char* key, int value, int* prev);
 // second MAS kernel (isp_mas2.cu): T2max <= 256, backpointer words in shared memory
 bool   mas2_supported(int B, int T1max, int T2max);
+bool   mas2_linkable(int B, int T1max, int T2max, int dbg);
+bool   mas_linkable(int B, int T1max, int T2max);
 size_t mas2_workspace_bytes(int B);
 int    mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text_len, const int64_t* mel_len,
                     int B, int T1max, int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws,
-                    int no_tma, int ring_rows, int slots, int dbg, cudaStream_t stream);
+                    int no_tma, int ring_rows, int slots, int dbg, cudaStream_t stream, const int* ready = nullptr, int ready_need = 0);
 int    mas2_set_option(const char* key, int value, int* prev);
 // general kernel for wide utterances (isp_mas_wide.cu): any T2max <= ISP_MAS_WIDE_MAX_T2
 bool   mas_wide_supported(int T2max);
@@ -36,7 +39,9 @@ int    mas_wide_forward(const float* logp, int64_t sB, int64_t sT1, const int64_
 size_t loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
                       int B, int T1max, int T2max, int D, float scale, int attention_prior,
-                      float* attn_logits, float* attn_soft, void* ws, size_t ws_bytes, cudaStream_t stream);
+                      float* attn_logits, float* attn_soft, void* ws, size_t ws_bytes, cudaStream_t stream, int* ready = nullptr);
+bool   loglik_supported(int T2max, int D, int dtype);
+int    loglik_tiles_per_utterance(int T1max);     // what `ready[b]` reaches when utterance b's outputs are complete
 int    loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                    float scale, int attention_prior, float* attn_logits, float* attn_soft, cudaStream_t stream);
 int    loglik_set_option(const char* key, int value, int* prev);

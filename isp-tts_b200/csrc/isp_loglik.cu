@@ -71,7 +71,23 @@ struct LoglikParams {
     int vec4;            // T2max % 4 == 0 and outputs 16 B aligned
     uint32_t idesc_base; // instruction descriptor without N
     int debug_scores;    // 1: write scale*S into `logits`, zeros into `soft`
+    unsigned long long* tstamp;   // debug (align.trace): [0] first CTA start, [1] last CTA end (%globaltimer), or nullptr
+    int* ready;          // per utterance: tiles whose outputs are complete (isp_align_forward: the MAS kernel waits on it), or nullptr
 };
+
+// isp_align_forward: the MAS kernel takes an utterance's attn_logits as soon as every frame tile of it is in global memory.
+// A release costs the round trip of the stores before it, and a CTA that waited for it at its end would hold its SM slot that
+// much longer (measured: +10 % on the kernel).  So the publishing is warp 0's job -- it has nothing to do once the MMAs are
+// issued: the epilogue warps arrive on a named barrier when their attn_logits stores are ISSUED (they go on to attn_soft), warp 0
+// waits on that barrier and counts the tile with a release.
+constexpr uint32_t kPublishBar = 6;
+ISP_DEVINL void publish_arrive() { asm volatile("bar.arrive %0, %1;" ::"r"(kPublishBar), "r"(kThreads) : "memory"); }
+ISP_DEVINL void publish_tile(int* ready, int b, int lane) {        // warp 0, converged
+    asm volatile("bar.sync %0, %1;" ::"r"(kPublishBar), "r"(kThreads) : "memory");
+    // (release at device scope, cumulative over the stores the barrier ordered before this thread)
+    if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ready + b) : "memory");
+    __syncwarp();
+}
 
 // ---- tcgen05 / TMA wrappers ---------------------------------------------------------
 ISP_DEVINL void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -217,6 +233,20 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // A kernel launched behind this one with programmatic stream serialisation (isp_mas_forward does, see isp_mas2.cu) may become
+    // resident on the SMs this grid's last wave leaves free and run its set-up there; it waits for this grid's completion
+    // (griddepcontrol.wait) before it touches global memory.  Without such a dependent this is a no-op.
+    if (p.tstamp != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(p.tstamp, t);
+    }
+    if (p.ready != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        // the linked MAS launch's time origin (the word behind the ready counts): unset until its first CTA starts
+        *reinterpret_cast<unsigned long long*>(p.ready + ((p.B + 1) & ~1)) = 0ull;
+        __threadfence();
+    }
+    asm volatile("griddepcontrol.launch_dependents;");
     // utterance-major launch order on purpose: it interleaves arithmetic tiles with the straight fills of padded tiles,
     // so the two kinds share an SM and HBM writes overlap the epilogue (tile-major order measured 4 % slower on cfg3)
     const int mt = blockIdx.x;       // frame tile
@@ -263,15 +293,33 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const size_t nelem = size_t(rows) * p.T2max;
         float* gl = p.logits + off;
         float* gs = p.soft + off;
-        if (p.vec4) {
-            const float4 c4 = make_float4(cst, cst, cst, cst), z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            const size_t n4 = nelem >> 2;
-            for (size_t idx = threadIdx.x; idx < n4; idx += kThreads) {
-                __stcs(reinterpret_cast<float4*>(gl) + idx, c4);
-                __stcs(reinterpret_cast<float4*>(gs) + idx, z4);
+        if (p.ready == nullptr) {
+            if (p.vec4) {
+                const float4 c4 = make_float4(cst, cst, cst, cst), z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const size_t n4 = nelem >> 2;
+                for (size_t idx = threadIdx.x; idx < n4; idx += kThreads) {
+                    __stcs(reinterpret_cast<float4*>(gl) + idx, c4);
+                    __stcs(reinterpret_cast<float4*>(gs) + idx, z4);
+                }
+            } else {
+                for (size_t idx = threadIdx.x; idx < nelem; idx += kThreads) { gl[idx] = cst; gs[idx] = 0.0f; }
             }
+            return;
+        }
+        // linked to the MAS kernel: attn_logits first, published by warp 0 while the others write attn_soft
+        if (p.vec4) {
+            const float4 c4 = make_float4(cst, cst, cst, cst);
+            for (size_t idx = threadIdx.x; idx < (nelem >> 2); idx += kThreads) __stcs(reinterpret_cast<float4*>(gl) + idx, c4);
         } else {
-            for (size_t idx = threadIdx.x; idx < nelem; idx += kThreads) { gl[idx] = cst; gs[idx] = 0.0f; }
+            for (size_t idx = threadIdx.x; idx < nelem; idx += kThreads) gl[idx] = cst;
+        }
+        if (warp == 0) publish_tile(p.ready, b, lane);
+        else publish_arrive();
+        if (p.vec4) {
+            const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (size_t idx = threadIdx.x; idx < (nelem >> 2); idx += kThreads) __stcs(reinterpret_cast<float4*>(gs) + idx, z4);
+        } else {
+            for (size_t idx = threadIdx.x; idx < nelem; idx += kThreads) gs[idx] = 0.0f;
         }
         return;
     }
@@ -308,6 +356,8 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
             umma_commit(mma_done);
         }
+        __syncwarp();
+        if (p.ready != nullptr) publish_tile(p.ready, b, lane);
     } else {
         // ============================ epilogue: two threads per frame ===================
         // Warps w and w + 4 share a TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ..) and split the
@@ -375,12 +425,14 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 const float cst = (half == 0 && p.prior) ? kLogPriorFloor - logf(float(p.T2max)) : 0.0f;
                 float* gout = (half == 0 ? g_logits : g_soft) + size_t(warp_row0) * p.T2max;
                 const int nelem = rows_valid * p.T2max;
+                if (p.ready != nullptr && half == 1) publish_arrive();         // (this warp writes attn_soft only)
                 if (vec4) {
                     const float4 c4v = make_float4(cst, cst, cst, cst);
                     for (int idx = lane; idx < (nelem >> 2); idx += 32) __stcs(reinterpret_cast<float4*>(gout) + idx, c4v);
                 } else {
                     for (int idx = lane; idx < nelem; idx += 32) gout[idx] = cst;
                 }
+                if (p.ready != nullptr && half == 0) publish_arrive();
             } else if (p.debug_scores) {
                 mbar_wait(mma_done, 0);
                 tc_fence_after();
@@ -397,6 +449,7 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     store_chunk(stage, g_soft, lane, warp_row0, rows_valid, ch * kCW, p.T2max, vec4);
                     __syncwarp();
                 }
+                if (p.ready != nullptr) publish_arrive();
             } else {
                 // ---- pass 0: the prior's row sum over this half's valid columns.  It does not depend on the scores, so it
                 // runs while the operands are still in flight (the wait for the MMA comes after it) -------------------
@@ -608,6 +661,7 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     store_chunk_fast(g_logits, j0);
                     __syncwarp();
                 }
+                if (p.ready != nullptr) publish_arrive();          // this warp's attn_logits stores are issued
 
                 // ---- pass 3: attn_soft = w / sum(w) on valid cells, 0 elsewhere -----------------
                 // (.w alone is written: the partner may still be reading x, y, z of the pass-1 exchange)
@@ -656,6 +710,11 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    if (p.tstamp != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(p.tstamp + 1, t);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -677,13 +736,33 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int g_opt_debug_scores = 0;
+static int g_opt_trace = 0;
 
 int loglik_set_option(const char* key, int value, int* prev) {
+    if (!strcmp(key, "align.trace")) { *prev = g_opt_trace; g_opt_trace = value; return 0; }
     if (!strcmp(key, "loglik.debug_scores")) { *prev = g_opt_debug_scores; g_opt_debug_scores = value; return 0; }
     return -1;
 }
 
 size_t loglik_workspace_bytes(int, int, int, int, int) { return 0; }
+// shared memory of one CTA: operand slabs, the epilogue's staging, the prior's table, the row-statistics exchange, barriers
+static size_t loglik_smem_bytes(int T2max, int D, int elem) {
+    const int npad = (T2max + 15) & ~15, nt = (npad + 255) / 256, boxrows_b = nt == 1 ? npad : 256, kslabs = (D * elem + 127) / 128;
+    return size_t(kslabs) * (kTileM * 128 + size_t(nt) * boxrows_b * 128)
+         + sizeof(float) * (kEpiWarps * 32 * kStagePitch + ((npad + 31) & ~31) + 4 * 2 * kTileM)
+         + sizeof(uint64_t) * (kMaxSlabs + 2) + 1024 /* base alignment slack */;
+}
+
+// does the fused kernel cover this shape?  (isp_loglik_supported: callers route the rest through isp_gemm_batched + isp_loglik_rows)
+bool loglik_supported(int T2max, int D, int dtype) {
+    if (dtype != ISP_DTYPE_F32 && dtype != ISP_DTYPE_BF16) return false;
+    const int elem = dtype == ISP_DTYPE_BF16 ? 2 : 4;
+    if (T2max <= 0 || D <= 0 || D % 8 != 0 || D > ISP_LOGLIK_MAX_D || T2max > ISP_LOGLIK_MAX_T2) return false;
+    if ((D * elem + 127) / 128 > kMaxSlabs) return false;
+    return loglik_smem_bytes(T2max, D, elem) <= 227 * 1024;
+}
+
+int loglik_tiles_per_utterance(int T1max) { return (T1max + kTileM - 1) / kTileM; }
 
 // operand tensor map: (D, T, B) elements, box (128 B worth of D, rows, 1), 128 B swizzle
 static int make_map(CUtensorMap* map, const void* base, int dtype, int D, int T, int B, int boxrows) {
@@ -703,7 +782,7 @@ static int make_map(CUtensorMap* map, const void* base, int dtype, int D, int T,
 
 int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
                    int B, int T1max, int T2max, int D, float scale, int attention_prior,
-                   float* attn_logits, float* attn_soft, void*, size_t, cudaStream_t stream) {
+                   float* attn_logits, float* attn_soft, void*, size_t, cudaStream_t stream, int* ready) {
     if (!Q || !K || !text_len || !mel_len || !attn_logits || !attn_soft) { set_error("isp_loglik_forward: null pointer"); return ISP_ERR_INVALID; }
     if (B <= 0 || T1max <= 0 || T2max <= 0 || D <= 0) { set_error("isp_loglik_forward: sizes must be positive"); return ISP_ERR_INVALID; }
     if (dtype != ISP_DTYPE_F32 && dtype != ISP_DTYPE_BF16) { set_error("isp_loglik_forward: dtype must be ISP_DTYPE_F32 or ISP_DTYPE_BF16"); return ISP_ERR_INVALID; }
@@ -728,6 +807,8 @@ int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_
     p.prior = attention_prior ? 1 : 0;
     p.vec4 = (T2max % 4 == 0 && (reinterpret_cast<uintptr_t>(attn_logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(attn_soft) & 15) == 0) ? 1 : 0;
     p.debug_scores = g_opt_debug_scores;
+    p.ready = ready;
+    p.tstamp = (ready != nullptr && g_opt_trace) ? reinterpret_cast<unsigned long long*>(ready + ((B + 1) & ~1)) + 1 : nullptr;
     const uint32_t fmt = dtype == ISP_DTYPE_BF16 ? 1u : 2u;          // UMMA F16F32Format: BF16 = 1, TF32 = 2
     p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(kTileM >> 4) << 24);   // D=f32, A/B K-major
     if (p.kslabs > kMaxSlabs) { set_error("isp_loglik_forward: D * elem = %d B exceeds %d B", D * elem, kMaxSlabs * 128); return ISP_ERR_UNSUPPORTED; }
@@ -738,9 +819,7 @@ int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_
     rc = make_map(&mk, K, dtype, D, T2max, B, p.boxrows_b);
     if (rc) return rc;
 
-    const size_t smem = size_t(p.kslabs) * (kTileM * 128 + size_t(p.nt) * p.boxrows_b * 128)
-                      + sizeof(float) * (kEpiWarps * 32 * kStagePitch + ((p.npad + 31) & ~31) + 4 * 2 * kTileM)
-                      + sizeof(uint64_t) * (kMaxSlabs + 2) + 1024 /* base alignment slack */;
+    const size_t smem = loglik_smem_bytes(T2max, D, elem);
     if (smem > 227 * 1024) { set_error("isp_loglik_forward: needs %zu B of shared memory (T2max=%d, D=%d)", smem, T2max, D); return ISP_ERR_UNSUPPORTED; }
 
     const dim3 grid((T1max + kTileM - 1) / kTileM, B);

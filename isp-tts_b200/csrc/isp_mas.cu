@@ -869,9 +869,18 @@ static int launch_one(const MasMaps& maps, const MasParams& p, const MasPlan& pl
     return 0;
 }
 
+// would mas_forward hand this shape to the kernel that takes isp_align_forward's ready counts?
+bool mas_linkable(int B, int T1max, int T2max) {
+    if (T2max > ISP_MAS_MAX_T2 || g_opt_impl == 3 || g_opt_impl == 1 || g_opt_bits_global || g_opt_slots == 3) return false;
+    return mas2_linkable(B, T1max, T2max, g_opt_dbg);
+}
+
 int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
                 const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
-                int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, size_t ws_bytes, cudaStream_t stream,
+                const int* ready, int ready_need) {
+    // (ready: isp_align_forward's per-utterance tile counts; only isp_mas2.cu starts before the kernel in front has completed,
+    // the other kernels are launched plainly behind it and find every count final)
     if (!logp || !text_len || !mel_len || !ws) { set_error("isp_mas_forward: null pointer"); return ISP_ERR_INVALID; }
     if (!attn_hard && !path) { set_error("isp_mas_forward: attn_hard may be NULL only when the path is returned (isp_mas_forward_path)"); return ISP_ERR_INVALID; }
     if (B <= 0 || T1max <= 0 || T2max <= 0) { set_error("isp_mas_forward: B, T1max, T2max must be positive"); return ISP_ERR_INVALID; }
@@ -890,7 +899,7 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
     const bool want2 = g_opt_impl != 1 && !g_opt_bits_global && g_opt_slots != 3;
     if (want2 && mas2_supported(B, T1max, T2max))
         return mas2_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws,
-                            g_opt_no_tma, g_opt_ring_rows, g_opt_slots, g_opt_dbg, stream);
+                            g_opt_no_tma, g_opt_ring_rows, g_opt_slots, g_opt_dbg, stream, ready, ready_need);
     if (g_opt_impl == 2) { set_error("isp_mas_forward: mas.impl=2 but T1max=%d T2max=%d is outside isp_mas2.cu's range", T1max, T2max); return ISP_ERR_UNSUPPORTED; }
     MasPlan pl;
     int rc = mas_plan(B, T1max, T2max, &pl);

@@ -113,6 +113,12 @@ struct Params {
     float pace_cycles_per_step;   // what a step of the longest chain is expected to take (0: no pacing of the loaders)
     int together;           // 1: the short member of a pair starts with the long one (tests)
     int linger;             // 1: every CTA is resident from the start, so a slot may outlive its sweep to keep the fill slow
+    int by_cost;            // 1: work items go to the CTAs in the order of their expected duration (0: of their length)
+    int early_lengths;      // 1: the lengths are not written by the grid in front of this one: they may be read before it completes
+    const int* ready;       // isp_align_forward: ready[b] reaches ready_need when utterance b's logits are in global memory (nullptr:
+    int ready_need;         // the logits are complete when the grid in front of this one is)
+    unsigned long long* origin;   // linked launches: %globaltimer of the first CTA to start (0 until then); the windows of the
+    float cycles_per_ns;          // paced loads and of the zero fill are counted from it, not from each CTA's own (staggered) start
 };
 
 struct Maps { CUtensorMap m[kNumBox]; };
@@ -171,6 +177,13 @@ ISP_DEVINL int lds_s16(uint32_t saddr) {
     short v;
     asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(saddr));
     return int(v);
+}
+// SM cycles since the launch's first CTA started (linked launches: the CTAs of this grid become resident one by one)
+ISP_DEVINL float cycles_since_origin(unsigned long long* origin, float cycles_per_ns) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    const unsigned long long old = atomicCAS(origin, 0ull, now);
+    return old == 0ull || now <= old ? 0.0f : float(now - old) * cycles_per_ns;
 }
 ISP_DEVINL long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 ISP_DEVINL void named_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
@@ -332,11 +345,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t smem_sa = smem_u32(smem_raw);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.status[0] = -2;                               // isp_mas_status: the per-utterance flags follow, there is no counter
-        p.status[1] = p.B;
-        if (p.probe != nullptr) p.probe[17] = gtimer();
-    }
+    // Programmatic dependent launch: this grid may have become resident while the grid in front of it in the stream (the
+    // log-likelihood kernel) is still draining.  Nothing in global memory is read or written before griddepcontrol.wait, except --
+    // when the caller vouches that the previous grid does not write them -- the lengths, so that the ranking, the geometry and the
+    // barrier set-up run under the previous kernel's tail.  (A no-op for a launch without the attribute.)
+    // With per-utterance ready counts (isp_align_forward) there is no wait at all: the logits are the only thing the grid in front
+    // produces, and a loader takes its utterance's rows as soon as their count is final -- the chains of this kernel start under
+    // the last wave of the log-likelihood kernel.
+    const bool linked = p.ready != nullptr && p.order == nullptr;
+    const bool early = linked || (p.early_lengths != 0 && p.order == nullptr);
+    if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // warps: [fillers x2][loaders 2 x 4][helpers 2 x 2][strips of slot 1][strips of slot 0] -- the chains get the highest ids
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,14 +365,17 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     else { role = 0; slot = warp < 18 ? 1 : 0; s = (warp - 14) & 3; }
 
     // ---- which utterances, and how the two share the SM ----
-    const int c = blockIdx.x;
-    int rank0, rank1 = -1;
-    if (c < p.nsingle) rank0 = c;
-    else { rank0 = c; rank1 = p.B - 1 - (c - p.nsingle); if (rank1 <= rank0) rank1 = -1; }
-    if (rank0 >= p.B) return;
+    int c = blockIdx.x;
+    int rank0 = 0, rank1 = -1;
+    auto members = [&](int cc, int& r0, int& r1) __attribute__((always_inline)) {
+        r0 = cc; r1 = -1;
+        if (cc >= p.nsingle) { r1 = p.B - 1 - (cc - p.nsingle); if (r1 <= r0) r1 = -1; }
+    };
     int b0, b1 = -1, blong;
     uint32_t key0 = 0, key1 = 0, keyl = 0;              // self-ranking: (frames << 17 | tokens - 1 << 9 | index'), clamped lengths
     if (p.order != nullptr) {
+        members(c, rank0, rank1);
+        if (rank0 >= p.B) return;
         if (slot == 1 && rank1 < 0) return;
         b0 = p.order[rank0];
         if (rank1 >= 0) b1 = p.order[rank1];
@@ -364,8 +385,11 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
         // its own -- B compares for each of B threads, ~1 us at B = 256, where a separate sorting kernel in front of this one
         // costs 6 us of launch and dependency.  Keys are unique (the index is part of them).
         uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw + kZeroPage + 2 * kHdr);
-        int* sel = reinterpret_cast<int*>(smem_raw + kZeroPage + kOffNegInf);      // (the -inf page is written after this)
         const int bp = (p.B + 3) & ~3;
+        int* byrank = reinterpret_cast<int*>(keys + bp);                            // utterance of every rank
+        uint32_t* cost = reinterpret_cast<uint32_t*>(byrank + bp);                  // per work item (CTA's worth of utterances)
+        int* sel = reinterpret_cast<int*>(smem_raw + kZeroPage + kOffNegInf);      // (the -inf page is written after this)
+        const int items = int(gridDim.x);
         for (int t = threadIdx.x; t < bp; t += kThreads) {
             uint32_t key = 0;
             if (t < p.B) {
@@ -383,14 +407,34 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
                 const uint4 ku = *reinterpret_cast<const uint4*>(keys + u);
                 r += (ku.x > kt) + (ku.y > kt) + (ku.z > kt) + (ku.w > kt);
             }
-            if (r == rank0) sel[0] = t;
-            if (r == rank1) sel[1] = t;
-            if (r == 0) sel[2] = t;
+            byrank[r] = t;
         }
         __syncthreads();
-        b0 = sel[0];
-        if (rank1 >= 0) b1 = sel[1];
-        blong = sel[2];
+        // Work items (the c-th longest alone, or with its short partner) are handed to the CTAs in the order of what they are
+        // expected to take, not of their length: CTAs become resident in blockIdx order -- one by one when this grid starts under
+        // the tail of the kernel in front of it, in waves when there are more CTAs than SMs -- and a long utterance that shares
+        // its SM runs ~15 % slower per step and has a longer tail than a longer one alone (measured at cfg3: 0.031 us per frame
+        // + 11 us alone, 0.036 us per frame + 15.6 us with a partner).
+        for (int cc = threadIdx.x; cc < items; cc += kThreads) {
+            int r0, r1;
+            members(cc, r0, r1);
+            const uint32_t k0 = keys[byrank[r0]];
+            const uint32_t steps = (k0 >> 17) + 31u + 51u * ((((k0 >> 9) & 0xffu) + 1u + 63u) / 64u - 1u);
+            cost[cc] = (r1 >= 0 ? 70u * steps + 29000u : 61u * steps + 20000u) * 1024u + uint32_t(items - 1 - cc);   // unique
+        }
+        __syncthreads();
+        for (int cc = threadIdx.x; cc < items; cc += kThreads) {
+            const uint32_t kc = cost[cc];
+            int pos = 0;
+            for (int u = 0; u < items; ++u) pos += cost[u] > kc;
+            if ((p.by_cost ? pos : cc) == int(blockIdx.x)) sel[0] = cc;
+        }
+        __syncthreads();
+        c = sel[0];
+        members(c, rank0, rank1);
+        b0 = byrank[rank0];
+        if (rank1 >= 0) b1 = byrank[rank1];
+        blong = byrank[0];
         key0 = keys[b0]; key1 = keys[b1 >= 0 ? b1 : b0]; keyl = keys[blong];
         __syncthreads();                                // the key scratch becomes the slots' bodies
         if (slot == 1 && rank1 < 0) return;
@@ -431,9 +475,18 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     float pace = 0.0f;
     if (p.linger && p.pace_cycles_per_step > 0.0f) {
         const Geo gl = from_keys ? make_geo(keyl >> 17, ((keyl >> 9) & 0xffu) + 1, p.T1max, p.T2max) : make_geo(p.mel_len[blong], p.text_len[blong], p.T1max, p.T2max);
-        const float t_long = float(gl.n + 31 + 51 * (gl.ns - 1)) * p.pace_cycles_per_step;
+        float t_long = float(gl.n + 31 + 51 * (gl.ns - 1)) * p.pace_cycles_per_step;
         // (the chains within a fifth of the longest are the ones being protected: they run free)
-        if (5 * g.n < 4 * gl.n) pace = t_long / float(g.nch + 3 * (g.ns - 1));
+        if (5 * g.n < 4 * gl.n) {
+            if (linked && role == 1) {
+                // a CTA that became resident late gets what is left of the longest chain's sweep, but no less than its own
+                const float own = float(g.n + 31 + 51 * (g.ns - 1)) * p.pace_cycles_per_step;
+                float el = lane == 0 ? cycles_since_origin(p.origin, p.cycles_per_ns) : 0.0f;
+                el = __shfl_sync(0xffffffffu, el, 0);
+                t_long = fmaxf(t_long - el, own);
+            }
+            pace = t_long / float(g.nch + 3 * (g.ns - 1));
+        }
     }
     const int n = g.n, m = g.m, nch = g.nch;
     const uint32_t hdr_sa = smem_sa + kZeroPage + uint32_t(slot) * kHdr;
@@ -476,10 +529,6 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     // ---- set-up: barriers, counters, exchange arrays, the zero rows in front of row 0 ----
     if (role == 0) {
         if (lane == 0) {
-            if (s == 0) {
-                const long long n64 = p.mel_len[b], m64 = p.text_len[b];
-                p.bad[b] = (unsigned char)(n64 < 1 || n64 > p.T1max || m64 < 1 || m64 > p.T2max);
-            }
             for (int st = 0; st < nstg; ++st) {
                 mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (full_s - smem_sa)) + st, p.tma ? 1 : 32);
                 mbar_init(reinterpret_cast<uint64_t*>(smem_raw + (empty_s - smem_sa)) + st, 1);
@@ -503,6 +552,16 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
         // ring rows 0..31 stand for rows -32..-1: zeros (any finite value keeps the accumulators at -inf)
         for (uint32_t i = lane; i < 2u * stageB / 16u; i += 32) *reinterpret_cast<uint4*>(smem_raw + (ring_s - smem_sa) + 16u * i) = make_uint4(0, 0, 0, 0);
         fence_proxy_async();                            // the TMA boxes overwrite them later
+    }
+    if (early && !linked) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (role == 0 && s == 0 && lane == 0) {
+        const long long n64 = p.mel_len[b], m64 = p.text_len[b];
+        p.bad[b] = (unsigned char)(n64 < 1 || n64 > p.T1max || m64 < 1 || m64 > p.T2max);
+        if (blockIdx.x == 0 && slot == 0) {
+            p.status[0] = -2;                           // isp_mas_status: the per-utterance flags follow, there is no counter
+            p.status[1] = p.B;
+            if (p.probe != nullptr) p.probe[17] = gtimer();
+        }
     }
     // the filler only announces itself: it needs nothing the others set up, and must not wait for a slot that starts late
     if (role == 2) asm volatile("bar.arrive %0, %1;" ::"r"(slot + 1), "r"(kSlotThreads) : "memory");
@@ -549,6 +608,20 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
             mbar_arrive_sa(full_s); mbar_arrive_sa(full_s + 8u);                         // (these barriers count the 32 lanes)
         }
         __syncwarp();
+        if (linked) {
+            // the utterance's logits: every frame tile published by the log-likelihood kernel (release / acquire at device scope);
+            // the TMA reads them through the async proxy, hence the proxy fence behind the acquire
+            uint32_t spins = 0;
+            int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.ready + b) : "memory");
+                if (seen >= p.ready_need) break;
+                __nanosleep(200);
+                if (++spins > (1u << 24)) __trap();
+            } while (true);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+        }
         if (!solo || lane == 0) {
             int issued = 0, landed = 0;
             int st_i = 2 % nstg, st_l = 2 % nstg;
@@ -620,7 +693,8 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
             // saturate HBM for the first third of the launch and starve the long chains that decide when it ends.
             const int pieces = int((size_t(ze - zb) + kZeroPage - 1) / kZeroPage);
             const float own = 0.8f * 45.0f * float(n + 31 + 51 * (g.ns - 1));           // most of this utterance's own sweep
-            const float rate = float(pieces) / fmaxf(p.fill_cycles, own);
+            const float window = linked ? p.fill_cycles - cycles_since_origin(p.origin, p.cycles_per_ns) : p.fill_cycles;
+            const float rate = float(pieces) / fmaxf(window, own);
             const long long t0 = clock64();
             int issued = 0;
             uint32_t idle = 0;
@@ -855,6 +929,9 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
         if (probe_w && lane == 0) { p.probe[3] = clock64(); p.probe[16] = gtimer(); }
         if (p.trace != nullptr && lane == 0) p.trace[4 * b + 1] = gtimer();
         __syncwarp();
+        // the utterance's ready count goes back to zero for the next isp_align_forward on this workspace (every loader of the
+        // utterance has long seen it final; the next call's increments come after this grid in stream order)
+        if (linked && lane == 0) const_cast<int*>(p.ready)[b] = 0;
         if (slot == 0 && lane == 0) st_release_sa(slot0_done_sa, 1);
     }
 }
@@ -908,6 +985,8 @@ static int g2_single = 0;
 static int g2_fill_us = 0;
 static int g2_together = 0;
 static int g2_pace = -1;
+static int g2_by_cost = 1;
+static int g2_pdl = 0;              // 0: plain launch; 1: programmatic stream serialisation; 2: ... and the lengths may be read early
 
 int mas2_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas2.min_pair_stages")) { *prev = g2_min_pair_stages; g2_min_pair_stages = value; return 0; }
@@ -915,7 +994,14 @@ int mas2_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas2.fill_us")) { *prev = g2_fill_us; g2_fill_us = value; return 0; }
     if (!strcmp(key, "mas2.together")) { *prev = g2_together; g2_together = value; return 0; }
     if (!strcmp(key, "mas2.pace")) { *prev = g2_pace; g2_pace = value; return 0; }
+    if (!strcmp(key, "mas2.by_cost")) { *prev = g2_by_cost; g2_by_cost = value; return 0; }
+    if (!strcmp(key, "mas.pdl")) { *prev = g2_pdl; g2_pdl = value; return 0; }
     return -1;
+}
+
+// isp_align_forward: does mas2_forward take the ready counts for this shape (the CTAs rank the batch themselves)?
+bool mas2_linkable(int B, int T1max, int T2max, int dbg) {
+    return mas2_supported(B, T1max, T2max) && B <= kRankMax && T1max < (1 << 14) && !(dbg & 128);
 }
 
 bool mas2_supported(int B, int T1max, int T2max) {
@@ -968,7 +1054,7 @@ static bool make_maps2(Maps* maps, const float* logp, int64_t sB, int64_t sT1, i
 
 int mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text_len, const int64_t* mel_len,
                  int B, int T1max, int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws,
-                 int no_tma, int ring_rows, int slots, int dbg, cudaStream_t stream) {
+                 int no_tma, int ring_rows, int slots, int dbg, cudaStream_t stream, const int* ready, int ready_need) {
     int sm_count = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -989,12 +1075,14 @@ int mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text
     p.max_stages = ring_rows > 0 ? (ring_rows + kR - 1) / kR : 0;
     if (p.max_stages > 0 && p.max_stages < 6) p.max_stages = 6;
     p.min_pair_stages = g2_min_pair_stages > 0 ? g2_min_pair_stages : 8;
+    int khz_launch = 1965000;
     {
         // the zero fill's window: what the launch is expected to take -- the longest chain, or its share of the bytes at 80 % of
         // HBM bandwidth when the batch needs several waves of CTAs
         static int khz_of[64] = {0};                     // the attribute query costs milliseconds
         if (dev >= 0 && dev < 64 && khz_of[dev] == 0) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev); khz_of[dev] = v > 0 ? v : 1965000; }
         const int khz = (dev >= 0 && dev < 64) ? khz_of[dev] : 1965000;
+        khz_launch = khz;
         const double chain_us = (double(T1max) + 31.0 + 50.0 * ((T2max + kStrip - 1) / kStrip - 1)) * 40.0 / (khz * 1e-3) + 5.0;
         const double waves = B > 2 * sm_count ? double(B) / (2.0 * sm_count) : 1.0;
         const double bytes_us = double(B) * T1max * T2max * 4.0 / (0.8 * 6.5e6) / waves;
@@ -1033,7 +1121,27 @@ int mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "mas2 plan kernel launch");
     }
-    mas2_kernel<<<grid, kThreads, kSmemTotal, stream>>>(maps, p);
+    p.early_lengths = g2_pdl >= 2 ? 1 : 0;
+    p.by_cost = g2_by_cost;
+    p.ready = ready; p.ready_need = ready_need;
+    // (the word behind the ready counts, 8 B aligned, cleared with them by isp_align_forward)
+    p.origin = ready ? reinterpret_cast<unsigned long long*>(const_cast<int*>(ready) + ((B + 1) & ~1)) : nullptr;
+    p.cycles_per_ns = float(khz_launch) * 1e-6f;
+    if (g2_pdl >= 1 || ready != nullptr) {
+        // programmatic stream serialisation: the grid may be scheduled while the previous one drains (it calls griddepcontrol.wait)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemTotal; cfg.stream = stream;
+        cudaLaunchAttribute at;
+        memset(&at, 0, sizeof(at));
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, mas2_kernel, maps, p);
+        if (e != cudaSuccess) return cuda_fail(e, "mas2_kernel launch (programmatic serialisation)");
+    } else {
+        mas2_kernel<<<grid, kThreads, kSmemTotal, stream>>>(maps, p);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mas2_kernel launch");
     return 0;
