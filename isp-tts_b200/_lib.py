@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libisp_tts_b200.so")
+# (ISP_TTS_B200_LIB: another build of the same library, for A/B timing of two builds on one box -- tools/ab_build.sh)
+SO_PATH = os.environ.get("ISP_TTS_B200_LIB") or os.path.join(_PKG, "libisp_tts_b200.so")
 
 ISP_DTYPE_F32 = 0
 ISP_DTYPE_BF16 = 1
@@ -86,6 +87,9 @@ def load():
     lib.isp_unpack_workspace_bytes.restype = c_sz
     lib.isp_unpack_operands.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp, c_sz, vp]
     lib.isp_unpack_operands.restype = c_int
+    if os.environ.get("ISP_TTS_B200_LIB") and not hasattr(lib, "isp_align_forward"):      # an older build under A/B timing
+        _lib = lib
+        return lib
     lib.isp_align_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.isp_align_workspace_bytes.restype = c_sz
     lib.isp_align_forward.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, f32, c_int, vp, vp, vp, vp, vp, vp, c_sz, c_int, vp]

@@ -113,7 +113,6 @@ struct Params {
     float pace_cycles_per_step;   // what a step of the longest chain is expected to take (0: no pacing of the loaders)
     int together;           // 1: the short member of a pair starts with the long one (tests)
     int linger;             // 1: every CTA is resident from the start, so a slot may outlive its sweep to keep the fill slow
-    int by_cost;            // 1: work items go to the CTAs in the order of their expected duration (0: of their length)
     int early_lengths;      // 1: the lengths are not written by the grid in front of this one: they may be read before it completes
     const int* ready;       // isp_align_forward: ready[b] reaches ready_need when utterance b's logits are in global memory (nullptr:
     int ready_need;         // the logits are complete when the grid in front of this one is)
@@ -365,7 +364,7 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     else { role = 0; slot = warp < 18 ? 1 : 0; s = (warp - 14) & 3; }
 
     // ---- which utterances, and how the two share the SM ----
-    int c = blockIdx.x;
+    const int c = blockIdx.x;
     int rank0 = 0, rank1 = -1;
     auto members = [&](int cc, int& r0, int& r1) __attribute__((always_inline)) {
         r0 = cc; r1 = -1;
@@ -387,9 +386,7 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
         uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw + kZeroPage + 2 * kHdr);
         const int bp = (p.B + 3) & ~3;
         int* byrank = reinterpret_cast<int*>(keys + bp);                            // utterance of every rank
-        uint32_t* cost = reinterpret_cast<uint32_t*>(byrank + bp);                  // per work item (CTA's worth of utterances)
         int* sel = reinterpret_cast<int*>(smem_raw + kZeroPage + kOffNegInf);      // (the -inf page is written after this)
-        const int items = int(gridDim.x);
         for (int t = threadIdx.x; t < bp; t += kThreads) {
             uint32_t key = 0;
             if (t < p.B) {
@@ -410,27 +407,6 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
             byrank[r] = t;
         }
         __syncthreads();
-        // Work items (the c-th longest alone, or with its short partner) are handed to the CTAs in the order of what they are
-        // expected to take, not of their length: CTAs become resident in blockIdx order -- one by one when this grid starts under
-        // the tail of the kernel in front of it, in waves when there are more CTAs than SMs -- and a long utterance that shares
-        // its SM runs ~15 % slower per step and has a longer tail than a longer one alone (measured at cfg3: 0.031 us per frame
-        // + 11 us alone, 0.036 us per frame + 15.6 us with a partner).
-        for (int cc = threadIdx.x; cc < items; cc += kThreads) {
-            int r0, r1;
-            members(cc, r0, r1);
-            const uint32_t k0 = keys[byrank[r0]];
-            const uint32_t steps = (k0 >> 17) + 31u + 51u * ((((k0 >> 9) & 0xffu) + 1u + 63u) / 64u - 1u);
-            cost[cc] = (r1 >= 0 ? 70u * steps + 29000u : 61u * steps + 20000u) * 1024u + uint32_t(items - 1 - cc);   // unique
-        }
-        __syncthreads();
-        for (int cc = threadIdx.x; cc < items; cc += kThreads) {
-            const uint32_t kc = cost[cc];
-            int pos = 0;
-            for (int u = 0; u < items; ++u) pos += cost[u] > kc;
-            if ((p.by_cost ? pos : cc) == int(blockIdx.x)) sel[0] = cc;
-        }
-        __syncthreads();
-        c = sel[0];
         members(c, rank0, rank1);
         b0 = byrank[rank0];
         if (rank1 >= 0) b1 = byrank[rank1];
@@ -554,15 +530,6 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
         fence_proxy_async();                            // the TMA boxes overwrite them later
     }
     if (early && !linked) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (role == 0 && s == 0 && lane == 0) {
-        const long long n64 = p.mel_len[b], m64 = p.text_len[b];
-        p.bad[b] = (unsigned char)(n64 < 1 || n64 > p.T1max || m64 < 1 || m64 > p.T2max);
-        if (blockIdx.x == 0 && slot == 0) {
-            p.status[0] = -2;                           // isp_mas_status: the per-utterance flags follow, there is no counter
-            p.status[1] = p.B;
-            if (p.probe != nullptr) p.probe[17] = gtimer();
-        }
-    }
     // the filler only announces itself: it needs nothing the others set up, and must not wait for a slot that starts late
     if (role == 2) asm volatile("bar.arrive %0, %1;" ::"r"(slot + 1), "r"(kSlotThreads) : "memory");
     else named_sync(slot + 1, kSlotThreads);
@@ -822,6 +789,15 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
 
     // =========================== mapper, then the backtrack proper =========================
     {
+        if (lane == 0) {
+            // (the keys hold the clamped lengths; the out-of-contract flag needs the originals -- read here, off the chains' warps)
+            const long long n64 = p.mel_len[b], m64 = p.text_len[b];
+            p.bad[b] = (unsigned char)(n64 < 1 || n64 > p.T1max || m64 < 1 || m64 > p.T2max);
+            if (blockIdx.x == 0 && slot == 0) {
+                p.status[0] = -2;                       // isp_mas_status: the per-utterance flags follow, there is no counter
+                p.status[1] = p.B;
+            }
+        }
         const int k = lane & 7, gq = lane >> 3;
         const int nq = (g.g1 + 3) >> 2;
         // plane k of the identity map, word w: bit b = bit k of (32 w + b).  k < 5: a pattern in b; k >= 5: all of bit (k - 5) of w.
@@ -985,7 +961,6 @@ static int g2_single = 0;
 static int g2_fill_us = 0;
 static int g2_together = 0;
 static int g2_pace = -1;
-static int g2_by_cost = 1;
 static int g2_pdl = 0;              // 0: plain launch; 1: programmatic stream serialisation; 2: ... and the lengths may be read early
 
 int mas2_set_option(const char* key, int value, int* prev) {
@@ -994,7 +969,6 @@ int mas2_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas2.fill_us")) { *prev = g2_fill_us; g2_fill_us = value; return 0; }
     if (!strcmp(key, "mas2.together")) { *prev = g2_together; g2_together = value; return 0; }
     if (!strcmp(key, "mas2.pace")) { *prev = g2_pace; g2_pace = value; return 0; }
-    if (!strcmp(key, "mas2.by_cost")) { *prev = g2_by_cost; g2_by_cost = value; return 0; }
     if (!strcmp(key, "mas.pdl")) { *prev = g2_pdl; g2_pdl = value; return 0; }
     return -1;
 }
@@ -1122,7 +1096,6 @@ int mas2_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text
         if (e != cudaSuccess) return cuda_fail(e, "mas2 plan kernel launch");
     }
     p.early_lengths = g2_pdl >= 2 ? 1 : 0;
-    p.by_cost = g2_by_cost;
     p.ready = ready; p.ready_need = ready_need;
     // (the word behind the ready counts, 8 B aligned, cleared with them by isp_align_forward)
     p.origin = ready ? reinterpret_cast<unsigned long long*>(const_cast<int*>(ready) + ((B + 1) & ~1)) : nullptr;
