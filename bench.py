@@ -550,9 +550,9 @@ def run_ours(args, w):
     # ---- next row: backward of the log-likelihood, measured beside the hot path ----------
     bwd = None
     if rank == 0 and not args.no_backward:
-        from isp_tts_b200.alignment import _scores, loglik_backward_ds
+        from isp_tts_b200.alignment import _scores, loglik_backward_ds, loglik_backward_from_logits
         from isp_tts_b200.gemm import bgemm
-        soft_b, logits_b = _loglik_cuda(q_dev, k_dev, tl_dev, ml_dev, scale, True)
+        soft_b, logits_b, rowsum_b = _loglik_cuda(q_dev, k_dev, tl_dev, ml_dev, scale, True, want_rowsum=True)
         gen = torch.Generator(device=dev).manual_seed(1)
         g_l = torch.randn(soft_b.shape, device=dev, generator=gen)
         g_s = torch.randn(soft_b.shape, device=dev, generator=gen)
@@ -565,6 +565,10 @@ def run_ours(args, w):
         def f_ds():
             box["ds"] = loglik_backward_ds(box["sc"], soft_b, g_l, g_s, scale, True, out_dtype=gemm_dtype)
 
+        def f_ds2():
+            # the product's route: dS from attn_logits and the prior's saved row sums -- no score GEMM, no attn_soft read
+            box["ds2"] = loglik_backward_from_logits(logits_b, g_l, g_s, rowsum_b, tl_dev, ml_dev, scale, True, out_dtype=gemm_dtype)
+
         def f_grads():
             box["gq"] = bgemm(box["ds"], k_dev, out_dtype=gemm_dtype, k_len=tl_dev)                  # dQ = dS.K   (K read MN-major)
             box["gk"] = bgemm(box["ds"].transpose(1, 2), q_dev, out_dtype=gemm_dtype, k_len=ml_dev)  # dK = dS^T.Q (both MN-major)
@@ -574,10 +578,24 @@ def run_ours(args, w):
             box["gq_l"] = torch.matmul(box["ds"], k_dev)
             box["gk_l"] = torch.matmul(box["ds"].transpose(1, 2), q_dev)
 
-        def f_all():
+        def f_all_scores():
             f_scores(); f_ds(); f_grads()
 
+        from_logits = rowsum_b is not None and T2 % 4 == 0
+
+        def f_all():
+            if from_logits:
+                f_ds2(); box["ds"] = box["ds2"]; f_grads()
+            else:
+                f_all_scores()
+
         t_s, t_ds, t_mm, t_lib = ([graph_ms(torch, f)] for f in (f_scores, f_ds, f_grads, f_lib))
+        t_all_scores = graph_ms(torch, f_all_scores)
+        t_ds2 = graph_ms(torch, f_ds2) if from_logits else None
+        if from_logits:
+            dd = float((box["ds2"].float() - box["ds"].float()).abs().max() / box["ds"].float().abs().max())
+            if dd > 2e-2:
+                raise RuntimeError("dS from attn_logits differs from dS from the recomputed scores: %g" % dd)
         t_all = graph_ms(torch, f_all)
         sc, d_s, gq, gk, gq_l, gk_l = box["sc"], box["ds"], box["gq"], box["gk"], box["gq_l"], box["gk_l"]
         gerr = max(float((gq.float() - gq_l.float()).abs().max() / gq_l.float().abs().max()),
@@ -592,7 +610,14 @@ def run_ours(args, w):
                "isp_gemm_batched_ms": {"scores_QKt": float(np.mean(t_s)), "dQ_and_dK": float(np.mean(t_mm))},
                "library_gemms_same_three_products_ms": float(np.mean(t_lib)),
                "max_rel_diff_vs_library": gerr, "padded_flops": fl_bwd,
-               "total_ms": float(t_all), "timing": "CUDA graph replay of each part and of the whole backward"}
+               "total_ms": float(t_all), "timing": "CUDA graph replay of each part and of the whole backward",
+               "route": ("isp_loglik_backward_from_logits + dQ, dK (what _LogLikelihood.backward runs)" if from_logits
+                         else "scores + isp_loglik_backward_ds + dQ, dK"),
+               "total_ms_scores_route": float(t_all_scores)}
+        if from_logits:
+            by2 = (12 + elem) * B * T1 * T2
+            bwd["isp_loglik_backward_from_logits"] = {"ms": float(t_ds2), "algorithmic_bytes": by2, "gbs": by2 / float(t_ds2) / 1e6,
+                                                      "max_rel_diff_vs_scores_route": dd}
         box.clear()
         del gq_l, gk_l
         # f-3: binarization loss from the path vs the reference's boolean-mask gather on the dense tensors (loss.py:97-105)
@@ -754,6 +779,8 @@ def run_ours(args, w):
     hbm_peak, tf_peak, which = load_peaks()
     if bwd is not None:
         bwd["isp_loglik_backward_ds"]["hbm_frac"] = bwd["isp_loglik_backward_ds"]["gbs"] / hbm_peak
+        if "isp_loglik_backward_from_logits" in bwd:
+            bwd["isp_loglik_backward_from_logits"]["hbm_frac"] = bwd["isp_loglik_backward_from_logits"]["gbs"] / hbm_peak
         bwd["f-3 length regulator"]["hbm_frac"] = bwd["f-3 length regulator"]["gbs"] / hbm_peak
         bwd["f-3 soft length regulator"]["hbm_frac"] = bwd["f-3 soft length regulator"]["gbs"] / hbm_peak
         bwd["f-3 soft averager"]["hbm_frac"] = bwd["f-3 soft averager"]["gbs"] / hbm_peak

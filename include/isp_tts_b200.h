@@ -164,6 +164,9 @@ int    isp_mas_status(const void* ws, void* stream);
  * scale             = attention_dim ** -0.5 (:116)
  * attn_logits, attn_soft  (B, T1max, T2max) fp32 contiguous, fully written (:208).
  * attention_prior   non-zero = the reference default (:194); 0 = plain scaled scores.
+ * ws                isp_loglik_workspace_bytes(...) = 4 * B * T1max bytes, 4 B aligned, or NULL with ws_bytes = 0: receives the
+ *                   row sums of the un-normalised prior, (B, T1max) fp32, valid frames only -- the one thing
+ *                   isp_loglik_backward_from_logits cannot re-derive bit for bit from attn_logits.
  * Limits: T2max <= ISP_LOGLIK_MAX_T2.
  * Accuracy: within 1e-3 relative of the fp32 reference (tests state the tolerance).
  */
@@ -189,7 +192,8 @@ int    isp_unpack_operands(const void* q_packed, const void* k_packed, int dtype
  * launched with programmatic stream serialisation, becomes resident on the SMs the last wave of the first kernel leaves
  * free, and each of its CTAs starts its utterance as soon as that utterance's count is final.  Arguments, outputs, limits and
  * results are those of the two separate calls (bit-identical); shapes the linked kernels do not cover run as the plain
- * sequence.  path may be NULL; attn_hard may be NULL when path is not.  ws: isp_align_workspace_bytes(...) bytes, 16 B aligned;
+ * sequence.  path may be NULL; attn_hard may be NULL when path is not.  prior_rowsum: (B, T1max) fp32 or NULL -- what
+ * isp_loglik_forward leaves in its workspace for isp_loglik_backward_from_logits.  ws: isp_align_workspace_bytes(...) bytes, 16 B aligned;
  * isp_mas_status(ws, stream) works on it as after isp_mas_forward.  flags: 0, or ISP_ALIGN_WS_CLEAN when the last thing that
  * touched ws was a successful isp_align_forward with the same B, T1max, T2max in the same stream (the call leaves its
  * counters cleared, so the next one needs no memset in front of the kernels: one graph node and ~3 us less per step). */
@@ -198,7 +202,7 @@ size_t isp_align_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    isp_align_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
                          int B, int T1max, int T2max, int D, float scale, int attention_prior,
                          float* attn_logits, float* attn_soft, int16_t* attn_hard, int64_t* durations, int16_t* path,
-                         void* ws, size_t ws_bytes, int flags, void* stream);
+                         float* prior_rowsum, void* ws, size_t ws_bytes, int flags, void* stream);
 /* 1 when isp_loglik_forward (and isp_align_forward's linked kernels) cover the shape: D a multiple of 8 and <= ISP_LOGLIK_MAX_D,
  * T2max <= ISP_LOGLIK_MAX_T2, and the operands of one frame tile plus one utterance's tokens fit in shared memory (fp32 operands
  * with several hundred tokens at D = 128 do not).  Other shapes: isp_gemm_batched for the scores, then isp_loglik_rows. */
@@ -232,6 +236,16 @@ int    isp_loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, con
 int    isp_loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
                               int B, int T1max, int T2max, float scale, int attention_prior,
                               void* dS, int ds_dtype, void* stream);
+
+/* The same gradient without the scores: from the forward's own attn_logits (alignment.py:196 read backwards --
+ * softmax_all(scale * S) = exp(attn_logits) / (prior + 1e-6), the prior in closed form from the row sums isp_loglik_forward
+ * left in its workspace -- and attn_soft recomputed as the masked softmax of attn_logits).  No score GEMM in front of it, no
+ * attn_soft read: 8-12 B/cell in, one launch less.  prior_rowsum (B, T1max) fp32 (may be NULL without attention_prior);
+ * text_len, mel_len as in the forward call; the other arguments as isp_loglik_backward_ds.  Only after the FUSED forward kernel
+ * (isp_loglik_forward / isp_align_forward): isp_loglik_rows evaluates the prior with other instructions. */
+int    isp_loglik_backward_from_logits(const float* attn_logits, const float* g_logits, const float* g_soft, const float* prior_rowsum,
+                                       const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max, float scale,
+                                       int attention_prior, void* dS, int ds_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batched, ragged GEMM on the tensor cores (tcgen05.mma, TMA operands, accumulator in TMEM):

@@ -156,7 +156,9 @@ def batch_diagonal_prior(text_lengths: Tensor, mel_lengths: Tensor, gamma: float
     return prior.masked_fill(prior < threshold, 0.0)
 
 
-def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool):
+def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool, want_rowsum: bool = False):
+    """(attn_soft, attn_logits) -- and, with want_rowsum, the prior's row sums (B, T1) the fused kernel leaves for the backward
+    pass (None when the shape went through the stand-alone row epilogue)."""
     dev = q.device
     _lib.require_device(dev)
     lib = _lib.load()
@@ -181,19 +183,22 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
             rc = lib.isp_loglik_rows(s.data_ptr(), s.stride(1), tl.data_ptr(), ml.data_ptr(), B, T1, T2, float(scale),
                                      1 if prior else 0, logits.data_ptr(), soft.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "isp_loglik_rows")
-        return soft, logits
+        return (soft, logits, None) if want_rowsum else (soft, logits)
+    rowsum = torch.empty((B, T1), dtype=torch.float32, device=dev) if want_rowsum else None
     with torch.cuda.device(dev):
         rc = lib.isp_loglik_forward(q.data_ptr(), k.data_ptr(), dt, tl.data_ptr(), ml.data_ptr(), B, T1, T2, D,
-                                    float(scale), 1 if prior else 0, logits.data_ptr(), soft.data_ptr(), None, 0,
+                                    float(scale), 1 if prior else 0, logits.data_ptr(), soft.data_ptr(),
+                                    rowsum.data_ptr() if rowsum is not None else None, 4 * B * T1 if rowsum is not None else 0,
                                     torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "isp_loglik_forward")
-    return soft, logits
+    return (soft, logits, rowsum) if want_rowsum else (soft, logits)
 
 
 def _align_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool, return_path: bool = False,
-                dense: bool = True):
+                dense: bool = True, want_rowsum: bool = False):
     """isp_align_forward: the log-likelihood kernel and the MAS kernel linked through per-utterance ready counts (the second
-    starts under the first's last wave).  Returns (soft, logits, hard, durations, path)."""
+    starts under the first's last wave).  Returns (soft, logits, hard, durations, path) -- and the prior's row sums for the
+    backward pass with want_rowsum (None when the fused log-likelihood kernel does not cover the shape)."""
     dev = q.device
     _lib.require_device(dev)
     lib = _lib.load()
@@ -209,7 +214,8 @@ def _align_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: 
     if not lib.isp_loglik_supported(T2, D, dt):
         soft, logits = _loglik_cuda(q, k, text_len, mel_len, scale, prior)
         out = mas_forward(logits, text_len, mel_len, durations=True, return_path=return_path, dense=dense)
-        return soft, logits, out[0], out[1], (out[2] if return_path else None)
+        res = (soft, logits, out[0], out[1], (out[2] if return_path else None))
+        return res + (None,) if want_rowsum else res
     q = q.contiguous()
     k = k.contiguous()
     tl = text_len.to(device=dev, dtype=torch.int64).contiguous()
@@ -221,17 +227,19 @@ def _align_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: 
     hard = torch.empty((B, T1, T2), dtype=torch.int16, device=dev) if dense else None
     dur = torch.empty((B, T2), dtype=torch.int64, device=dev)
     path = torch.empty((B, T1), dtype=torch.int16, device=dev) if return_path else None
+    rowsum = torch.empty((B, T1), dtype=torch.float32, device=dev) if want_rowsum else None
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         ws, clean = _align_workspace(lib, dev, stream, B, T1, T2, D, dt)
         rc = lib.isp_align_forward(q.data_ptr(), k.data_ptr(), dt, tl.data_ptr(), ml.data_ptr(), B, T1, T2, D, float(scale),
                                    1 if prior else 0, logits.data_ptr(), soft.data_ptr(), hard.data_ptr() if hard is not None else None,
-                                   dur.data_ptr(), path.data_ptr() if path is not None else None, ws.data_ptr(), ws.numel(),
+                                   dur.data_ptr(), path.data_ptr() if path is not None else None,
+                                   rowsum.data_ptr() if rowsum is not None else None, ws.data_ptr(), ws.numel(),
                                    _lib.ISP_ALIGN_WS_CLEAN if clean else 0, stream)
     if rc != 0:
         _ALIGN_WS.clear()
     _lib.check(rc, "isp_align_forward")
-    return soft, logits, hard, dur, path
+    return (soft, logits, hard, dur, path, rowsum) if want_rowsum else (soft, logits, hard, dur, path)
 
 
 # Workspaces of the linked call, one per (device, stream, shape): a workspace that only ever saw successful calls of one shape in
@@ -369,6 +377,33 @@ def loglik_backward_ds(scores: Tensor, soft: Tensor, g_logits: Tensor | None, g_
     return ds[:, :, :T2] if pad else ds
 
 
+def loglik_backward_from_logits(logits: Tensor, g_logits: Tensor | None, g_soft: Tensor | None, rowsum: Tensor | None,
+                                text_len: Tensor, mel_len: Tensor, scale: float, prior: bool,
+                                out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """dL/dS from the incoming gradients and the forward's own attn_logits (isp_loglik_backward_from_logits): no score GEMM, no
+    attn_soft read.  rowsum: the prior's row sums the fused forward kernel saved.  T2max % 4 == 0."""
+    dev = logits.device
+    _lib.require_device(dev)
+    lib = _lib.load()
+    B, T1, T2 = logits.shape
+    lg = logits.detach().float().contiguous()
+    gl = g_logits.float().contiguous() if g_logits is not None else None
+    gs = g_soft.float().contiguous() if g_soft is not None else None
+    tl = text_len.to(device=dev, dtype=torch.int64).contiguous()
+    ml = mel_len.to(device=dev, dtype=torch.int64).contiguous()
+    if prior and (rowsum is None or tuple(rowsum.shape) != (B, T1) or rowsum.dtype != torch.float32 or not rowsum.is_contiguous()):
+        raise ValueError("rowsum must be the contiguous float32 (B, T1max) tensor the fused forward kernel wrote")
+    ds = torch.empty((B, T1, T2), dtype=out_dtype, device=dev)
+    dt = _lib.ISP_DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
+    with torch.cuda.device(dev):
+        rc = lib.isp_loglik_backward_from_logits(lg.data_ptr(), gl.data_ptr() if gl is not None else None,
+                                                 gs.data_ptr() if gs is not None else None, rowsum.data_ptr() if rowsum is not None else None,
+                                                 tl.data_ptr(), ml.data_ptr(), B, T1, T2, float(scale), 1 if prior else 0, ds.data_ptr(), dt,
+                                                 torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "isp_loglik_backward_from_logits")
+    return ds
+
+
 class _LogLikelihood(torch.autograd.Function):
     """forward: the fused sm_100a kernel.  backward: three launches of the tcgen05 batched GEMM
     (isp_gemm_batched) around the one-pass Jacobian kernel (isp_loglik_backward_ds) -- scores S = Q.K^T recomputed,
@@ -381,21 +416,31 @@ class _LogLikelihood(torch.autograd.Function):
         ctx.scale, ctx.prior, ctx.with_mas = scale, prior, with_mas
         if with_mas:
             # the linked call (isp_align_forward): the hard path and the durations come with it, outside autograd
-            soft, logits, hard, dur, _ = _align_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior)
-            ctx.save_for_backward(q, k, soft, text_len, mel_len)
+            soft, logits, hard, dur, _, rowsum = _align_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior, want_rowsum=True)
+        else:
+            soft, logits, rowsum = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior, want_rowsum=True)
+        # The backward pass works from attn_logits and the prior's row sums when the fused kernel produced them (no score GEMM, no
+        # attn_soft read); otherwise (stand-alone row epilogue, token axis not a multiple of 4) from recomputed scores and attn_soft.
+        ctx.from_logits = rowsum is not None and logits.shape[2] % 4 == 0
+        if ctx.from_logits:
+            ctx.save_for_backward(q, k, logits, rowsum, text_len, mel_len)
+        else:
+            ctx.save_for_backward(q, k, soft, None, text_len, mel_len)
+        if with_mas:
             ctx.mark_non_differentiable(hard, dur)
             return soft, logits, hard, dur
-        soft, logits = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior)
-        ctx.save_for_backward(q, k, soft, text_len, mel_len)
         return soft, logits
 
     @staticmethod
     def backward(ctx, g_soft, g_logits, *_):
-        q, k, soft, text_len, mel_len = ctx.saved_tensors
+        q, k, saved, rowsum, text_len, mel_len = ctx.saved_tensors
         if g_soft is None and g_logits is None:
             return None, None, None, None, None, None, None
         qd, kd = q.detach().contiguous(), k.detach().contiguous()
-        d_s = loglik_backward_ds(_scores(qd, kd, text_len, mel_len), soft, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
+        if ctx.from_logits:
+            d_s = loglik_backward_from_logits(saved, g_logits, g_soft, rowsum, text_len, mel_len, ctx.scale, ctx.prior, out_dtype=q.dtype)
+        else:
+            d_s = loglik_backward_ds(_scores(qd, kd, text_len, mel_len), saved, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
         gq = bgemm(d_s, kd, out_dtype=q.dtype, k_len=text_len) if ctx.needs_input_grad[0] else None
         gk = bgemm(d_s.transpose(1, 2), qd, out_dtype=k.dtype, k_len=mel_len) if ctx.needs_input_grad[1] else None
         return gq, gk, None, None, None, None, None

@@ -101,7 +101,7 @@ size_t isp_align_workspace_bytes(int B, int T1max, int T2max, int D, int dtype) 
 
 int isp_align_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
                       int B, int T1max, int T2max, int D, float scale, int attention_prior,
-                      float* attn_logits, float* attn_soft, int16_t* attn_hard, int64_t* durations, int16_t* path,
+                      float* attn_logits, float* attn_soft, int16_t* attn_hard, int64_t* durations, int16_t* path, float* prior_rowsum,
                       void* ws, size_t ws_bytes, int flags, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!ws || B <= 0 || T1max <= 0 || T2max <= 0) { isp::set_error("isp_align_forward: null workspace or non-positive sizes"); return ISP_ERR_INVALID; }
@@ -120,7 +120,7 @@ int isp_align_forward(const void* Q, const void* K, int dtype, const int64_t* te
         if (e != cudaSuccess) return isp::cuda_fail(e, "cudaMemsetAsync(ready counts)");
     }
     int rc = isp::loglik_forward(Q, K, dtype, text_len, mel_len, B, T1max, T2max, D, scale, attention_prior, attn_logits, attn_soft,
-                                 nullptr, 0, st, link ? ready : nullptr);
+                                 prior_rowsum, prior_rowsum ? size_t(B) * T1max * sizeof(float) : 0, st, link ? ready : nullptr);
     if (rc) return rc;
     rc = isp::mas_forward(attn_logits, int64_t(T1max) * T2max, T2max, 1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path,
                           ws, off, st, link && g_align_mode == 0 ? ready : nullptr, isp::loglik_tiles_per_utterance(T1max));
@@ -144,6 +144,13 @@ int isp_loglik_forward(const void* Q, const void* K, int dtype, const int64_t* t
 int isp_loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                     float scale, int attention_prior, float* attn_logits, float* attn_soft, void* stream) {
     return isp::loglik_rows(S, ldS, text_len, mel_len, B, T1max, T2max, scale, attention_prior, attn_logits, attn_soft, static_cast<cudaStream_t>(stream));
+}
+
+int isp_loglik_backward_from_logits(const float* attn_logits, const float* g_logits, const float* g_soft, const float* prior_rowsum,
+                                    const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max, float scale,
+                                    int attention_prior, void* dS, int ds_dtype, void* stream) {
+    return isp::loglik_backward_from_logits(attn_logits, g_logits, g_soft, prior_rowsum, text_len, mel_len, B, T1max, T2max, scale,
+                                            attention_prior, dS, ds_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int isp_loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,

@@ -48,6 +48,10 @@ int    loglik_set_option(const char* key, int value, int* prev);
 int    loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
                           int B, int T1max, int T2max, float scale, int attention_prior, void* dS, int ds_dtype, cudaStream_t stream);
 
+int    loglik_backward_from_logits(const float* attn_logits, const float* g_logits, const float* g_soft, const float* prior_rowsum,
+                                   const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max, float scale,
+                                   int attention_prior, void* dS, int ds_dtype, cudaStream_t stream);
+
 int    length_regulate(const void* x, const int16_t* path, void* out, int dtype, int B, int T1max, int T2max, int C, cudaStream_t stream);
 int    length_regulate_backward(const float* g, const int64_t* durations, const int64_t* starts, float* gx,
                                 int B, int T1max, int T2max, int C, cudaStream_t stream);

@@ -36,6 +36,7 @@
 
 #include "common.cuh"
 #include "isp_internal.h"
+#include "isp_prior.cuh"
 
 namespace isp {
 
@@ -45,13 +46,6 @@ constexpr int kStagePitch = 20;                 // words per staged row: 16 B al
 constexpr int kEpiWarps = 8;                    // two per TMEM lane quadrant
 constexpr int kThreads = 32 * (1 + kEpiWarps);
 constexpr int kMaxSlabs = 8;                    // 128 B-wide K-slabs (D * elem <= 1024 B)
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kLogPriorFloor = -13.815510557964274f;   // log(1e-6)
-constexpr float kPriorEps = 1e-6f;
-constexpr float kPriorThreshold = 1e-4f;                 // alignment.py:18
-constexpr float kNegInvTwoGammaSq = -50.0f;              // -1 / (2 * 0.1^2)
-constexpr float kPriorScale = 8.493218002880191f;        // sqrt(50 log2 e): exp(-50 x^2) = 2^(-(kPriorScale x)^2)
 
 struct LoglikParams {
     const int64_t* text_len;
@@ -71,6 +65,7 @@ struct LoglikParams {
     int vec4;            // T2max % 4 == 0 and outputs 16 B aligned
     uint32_t idesc_base; // instruction descriptor without N
     int debug_scores;    // 1: write scale*S into `logits`, zeros into `soft`
+    float* psum_out;     // (B, T1max) row sums of the raw prior for the backward kernel (valid frames only are written), or nullptr
     unsigned long long* tstamp;   // debug (align.trace): [0] first CTA start, [1] last CTA end (%globaltimer), or nullptr
     int* ready;          // per utterance: tiles whose outputs are complete (isp_align_forward: the MAS kernel waits on it), or nullptr
 };
@@ -190,11 +185,6 @@ ISP_DEVINL void tmem_st16(uint32_t taddr, const float (&v)[16]) {
           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-ISP_DEVINL float fast_ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 ISP_DEVINL float fast_lg2(float x) {
     float y;
@@ -529,6 +519,8 @@ loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     psum = half == 0 ? psum + o.z : o.z + psum;       // the same order of addition in both halves
                     m = mn;
                 }
+                // the backward pass re-derives the prior's cells from this sum (isp_loglik_backward_from_logits)
+                if (p.psum_out != nullptr && half == 0 && row_valid) p.psum_out[size_t(b) * p.T1max + i] = psum;
                 if (T2b < p.T2max) {
                     // padded text columns have S == 0 exactly: add them in closed form
                     const float mn = fmaxf(m, 0.0f);
@@ -744,7 +736,8 @@ int loglik_set_option(const char* key, int value, int* prev) {
     return -1;
 }
 
-size_t loglik_workspace_bytes(int, int, int, int, int) { return 0; }
+// the workspace receives the prior's row sums, one float per frame (what isp_loglik_backward_from_logits takes)
+size_t loglik_workspace_bytes(int B, int T1max, int, int, int) { return B > 0 && T1max > 0 ? size_t(B) * T1max * sizeof(float) : 0; }
 // shared memory of one CTA: operand slabs, the epilogue's staging, the prior's table, the row-statistics exchange, barriers
 static size_t loglik_smem_bytes(int T2max, int D, int elem) {
     const int npad = (T2max + 15) & ~15, nt = (npad + 255) / 256, boxrows_b = nt == 1 ? npad : 256, kslabs = (D * elem + 127) / 128;
@@ -782,7 +775,7 @@ static int make_map(CUtensorMap* map, const void* base, int dtype, int D, int T,
 
 int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
                    int B, int T1max, int T2max, int D, float scale, int attention_prior,
-                   float* attn_logits, float* attn_soft, void*, size_t, cudaStream_t stream, int* ready) {
+                   float* attn_logits, float* attn_soft, void* ws, size_t ws_bytes, cudaStream_t stream, int* ready) {
     if (!Q || !K || !text_len || !mel_len || !attn_logits || !attn_soft) { set_error("isp_loglik_forward: null pointer"); return ISP_ERR_INVALID; }
     if (B <= 0 || T1max <= 0 || T2max <= 0 || D <= 0) { set_error("isp_loglik_forward: sizes must be positive"); return ISP_ERR_INVALID; }
     if (dtype != ISP_DTYPE_F32 && dtype != ISP_DTYPE_BF16) { set_error("isp_loglik_forward: dtype must be ISP_DTYPE_F32 or ISP_DTYPE_BF16"); return ISP_ERR_INVALID; }
@@ -808,6 +801,7 @@ int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_
     p.vec4 = (T2max % 4 == 0 && (reinterpret_cast<uintptr_t>(attn_logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(attn_soft) & 15) == 0) ? 1 : 0;
     p.debug_scores = g_opt_debug_scores;
     p.ready = ready;
+    p.psum_out = (ws != nullptr && ws_bytes >= size_t(B) * T1max * sizeof(float) && (reinterpret_cast<uintptr_t>(ws) & 3) == 0) ? static_cast<float*>(ws) : nullptr;
     p.tstamp = (ready != nullptr && g_opt_trace) ? reinterpret_cast<unsigned long long*>(ready + ((B + 1) & ~1)) + 1 : nullptr;
     const uint32_t fmt = dtype == ISP_DTYPE_BF16 ? 1u : 2u;          // UMMA F16F32Format: BF16 = 1, TF32 = 2
     p.idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(kTileM >> 4) << 24);   // D=f32, A/B K-major

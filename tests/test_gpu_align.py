@@ -76,16 +76,20 @@ def test_dirty_workspace_without_the_clean_flag(cuda_device):
     soft = torch.empty_like(logits)
     hard = torch.empty((B, T1, T2), dtype=torch.int16, device=cuda_device)
     dur = torch.empty((B, T2), dtype=torch.int64, device=cuda_device)
+    rowsum = torch.empty((B, T1), dtype=torch.float32, device=cuda_device)
+    ref_rowsum = _loglik_cuda(q, k, tlt, mlt, D ** -0.5, True, want_rowsum=True)[2]
+    valid = torch.arange(T1, device=cuda_device)[None] < mlt[:, None]
     st = torch.cuda.current_stream().cuda_stream
     for flags in (0, _lib.ISP_ALIGN_WS_CLEAN, _lib.ISP_ALIGN_WS_CLEAN):
         rc = lib.isp_align_forward(q.data_ptr(), k.data_ptr(), _lib.ISP_DTYPE_BF16, tlt.data_ptr(), mlt.data_ptr(), B, T1, T2, D, D ** -0.5, 1,
-                                   logits.data_ptr(), soft.data_ptr(), hard.data_ptr(), dur.data_ptr(), None, ws.data_ptr(), nb, flags, st)
+                                   logits.data_ptr(), soft.data_ptr(), hard.data_ptr(), dur.data_ptr(), None, rowsum.data_ptr(), ws.data_ptr(), nb, flags, st)
         assert rc == 0, lib.isp_last_error()
         torch.cuda.synchronize()
         assert torch.equal(logits, ref[1]) and torch.equal(soft, ref[0]) and torch.equal(hard, ref[2]) and torch.equal(dur, ref[3])
+        assert torch.equal(rowsum[valid], ref_rowsum[valid])          # the prior's row sums for the backward pass (valid frames)
         assert lib.isp_mas_status(ws.data_ptr(), st) == 0
     assert lib.isp_align_forward(q.data_ptr(), k.data_ptr(), _lib.ISP_DTYPE_BF16, tlt.data_ptr(), mlt.data_ptr(), B, T1, T2, D, D ** -0.5, 1,
-                                 logits.data_ptr(), soft.data_ptr(), hard.data_ptr(), dur.data_ptr(), None, ws.data_ptr(), nb - 1, 0, st) != 0
+                                 logits.data_ptr(), soft.data_ptr(), hard.data_ptr(), dur.data_ptr(), None, None, ws.data_ptr(), nb - 1, 0, st) != 0
 
 
 def test_linked_inside_a_cuda_graph(cuda_device):

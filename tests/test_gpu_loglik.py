@@ -147,9 +147,11 @@ def test_shapes_beyond_the_fused_kernel(cuda_device, shape, dtype):
     assert np.abs(l2 - r2l).max() < 5e-3 and np.abs(s2 - r2s).max() < 2e-3
 
 
-def test_backward_matches_torch_autograd(cuda_device):
-    """Gradients of (attn_soft, attn_logits) w.r.t. q, k against a plain torch restatement."""
-    B, T1, T2, D = 3, 70, 24, 32
+@pytest.mark.parametrize("T2", [24, 37])
+def test_backward_matches_torch_autograd(cuda_device, T2):
+    """Gradients of (attn_soft, attn_logits) w.r.t. q, k against a plain torch restatement, on both routes of the backward pass:
+    from attn_logits and the saved prior row sums (T2 = 24) and from recomputed scores (T2 = 37: a token axis that needs padding)."""
+    B, T1, D = 3, 70, 32
     tl, ml = synth.lengths(B, T2, T1, True, 3)
     qn, kn = synth.encoded_pair(B, T1, T2, D, tl, ml, 4)
     tlt, mlt = torch.from_numpy(tl).to(cuda_device), torch.from_numpy(ml).to(cuda_device)
@@ -208,6 +210,54 @@ def test_backward_ds_kernel(cuda_device, T2, which):
         assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (T2, which, prior, err)
         out16 = loglik_backward_ds(s, soft.detach(), gl, gs, scale, prior, out_dtype=torch.bfloat16)
         assert (out16.double() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(3, 130, 200, 64), (5, 260, 24, 32), (2, 300, 512, 32), (40, 200, 100, 64)])
+@pytest.mark.parametrize("which", ["both", "logits", "soft"])
+def test_backward_from_logits_kernel(cuda_device, shape, which):
+    """isp_loglik_backward_from_logits (no scores, no attn_soft: attn_logits and the prior's saved row sums) against the
+    closed-form Jacobians in fp64 on the TRUE scores, with and without the prior, ragged lengths, padded frames and tokens
+    included.  Tolerance: 1e-4 of the largest entry -- attn_logits carries the forward kernel's own rounding (tf32 products are
+    NOT in it: the Jacobian is taken at the scores the forward actually used, recovered from its logits)."""
+    from isp_tts_b200.alignment import _loglik_cuda, loglik_backward_from_logits
+    B, T1, T2, D = shape
+    tl, ml = synth.lengths(B, T2, T1, True, 7)
+    qn, kn = synth.encoded_pair(B, T1, T2, D, tl, ml, 8)
+    q, k = torch.from_numpy(qn).to(cuda_device), torch.from_numpy(kn).to(cuda_device)
+    tlt, mlt = torch.from_numpy(tl).to(cuda_device), torch.from_numpy(ml).to(cuda_device)
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    gl = torch.randn((B, T1, T2), device=cuda_device, generator=gen) if which != "soft" else None
+    gs = torch.randn((B, T1, T2), device=cuda_device, generator=gen) if which != "logits" else None
+    scale = D ** -0.5
+    for prior in (True, False):
+        soft, logits, rowsum = _loglik_cuda(q, k, tlt, mlt, scale, prior, want_rowsum=True)
+        assert rowsum is not None and rowsum.shape == (B, T1)
+        # the scores the forward kernel worked with, from its own output (so that its TF32 rounding is not counted as an error of
+        # the backward kernel): scale * S = attn_logits - log(prior + 1e-6) + lse, and softmax is invariant to the per-row lse
+        if prior:
+            from isp_tts_b200.alignment import batch_diagonal_prior
+            pr = batch_diagonal_prior(tlt, mlt, max_text=T2, max_mel=T1).double()
+            s_eff = (logits.double() - torch.log(pr + 1e-6)) / scale
+        else:
+            s_eff = logits.double() / scale
+        ref = _torch_ds(s_eff, soft, gl, gs, scale, prior)
+        out = loglik_backward_from_logits(logits, gl, gs, rowsum, tlt, mlt, scale, prior)
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        diff = (out.double() - ref).abs()
+        # cells whose prior sits within rounding of the 1e-4 threshold may be thresholded differently by torch's fp32 prior
+        if prior:
+            raw = pr * 0 + batch_diagonal_prior(tlt, mlt, threshold=0.0, max_text=T2, max_mel=T1).double()
+            amb = (raw - 1e-4).abs() < 2e-8
+            rows_amb = amb.any(dim=2, keepdim=True).expand_as(diff)
+            diff = diff.masked_fill(rows_amb, 0.0)
+            assert float(rows_amb[:, :, 0].double().mean()) < 0.03
+        err = diff.max().item()
+        assert err <= 1e-4 * max(1.0, ref.abs().max().item()), (shape, which, prior, err)
+        out16 = loglik_backward_from_logits(logits, gl, gs, rowsum, tlt, mlt, scale, prior, out_dtype=torch.bfloat16)
+        d16 = (out16.double() - ref).abs()
+        if prior:
+            d16 = d16.masked_fill(rows_amb, 0.0)
+        assert d16.max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
 
 
 def test_backward_bf16_operands(cuda_device):

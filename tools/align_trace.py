@@ -29,7 +29,7 @@ for it in range(4):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     rc = lib.isp_align_forward(qd.data_ptr(), kd.data_ptr(), 1, tlt.data_ptr(), mlt.data_ptr(), B, T1, T2, D, D ** -0.5, 1, logits.data_ptr(),
-                               soft.data_ptr(), hard.data_ptr(), dur.data_ptr(), None, ws.data_ptr(), nb, 1, st)
+                               soft.data_ptr(), hard.data_ptr(), dur.data_ptr(), None, None, ws.data_ptr(), nb, 1, st)
     assert rc == 0, lib.isp_last_error()
     e.record(); torch.cuda.synchronize()
 print(f"{w.name}: align call {s.elapsed_time(e)*1e3:.1f} us")
