@@ -47,7 +47,8 @@ extern "C" {
 #define ISP_DTYPE_F16  2          /* fp16 in memory, fp32 accumulate (isp_gemm_batched and its element-wise companions only) */
 
 #define ISP_MAS_MAX_T2   640      /* text tokens per utterance the fast (strip) MAS kernels cover */
-#define ISP_MAS_WIDE_MAX_T2 16384 /* beyond ISP_MAS_MAX_T2 a general, slower kernel runs: up to this many tokens */
+#define ISP_MAS_CLUSTER_MAX_T2 1024 /* beyond ISP_MAS_MAX_T2: one thread-block cluster per utterance (up to 8 CTAs of 128 tokens, DSMEM) */
+#define ISP_MAS_WIDE_MAX_T2 16384 /* beyond ISP_MAS_CLUSTER_MAX_T2 a general, slower kernel runs: up to this many tokens */
 #define ISP_LOGLIK_MAX_T2 512     /* text tokens per utterance the fused GEMM covers (TMEM columns) */
 #define ISP_LOGLIK_MAX_D  256     /* attention_dim */
 
@@ -77,8 +78,10 @@ int         isp_device_check(void);
  * ws        isp_mas_workspace_bytes(B,T1max,T2max) bytes, 16 B aligned; holds the status word,
  *           the packed backpointer bits when they do not fit in shared memory, and the
  *           path's column per frame until the zero-fill of attn_hard has landed.
- * Limits:   T2max <= ISP_MAS_WIDE_MAX_T2 (above ISP_MAS_MAX_T2 = 640 tokens a general kernel runs: one barrier per frame
- *           row instead of the strip wavefront, same results); T1max < 2^24.
+ * Limits:   T2max <= ISP_MAS_WIDE_MAX_T2.  Up to ISP_MAS_MAX_T2 = 640 tokens an utterance runs on one SM (strip wavefront);
+ *           641 .. ISP_MAS_CLUSTER_MAX_T2 = 1024 tokens on a thread-block cluster, the strip boundary and the backtrack maps
+ *           crossing CTAs through distributed shared memory (T1max <= ~8000 frames: the backpointer bits stay in shared
+ *           memory); beyond, a general kernel (one barrier per frame row).  Same results everywhere.  T1max < 2^24.
  * Results are bit-identical to the reference for NaN-free input.
  */
 size_t isp_mas_workspace_bytes(int B, int T1max, int T2max);
@@ -304,6 +307,9 @@ int    isp_instance_norm_apply(const void* y, int dtype, const float* stats, int
  *   "mas.no_tma"         1: 4 B async copies instead of tiled TMA boxes (the path taken when the
  *                        logits are not 16 B aligned or T2max is not a multiple of 4)
  *   "mas.dbg"            profiling switches, see isp_mas.cu
+ *   "mas.impl"           0: the kernel the shape calls for; 1: isp_mas.cu; 2: isp_mas2.cu or fail; 3: isp_mas_wide.cu;
+ *                        4: isp_mas_cluster.cu or fail (tests force each kernel onto every shape it covers)
+ *   "masc.trace"         1: the cluster kernel leaves phase timestamps in the workspace (tools/masc_probe.py)
  * Returns the previous value, or ISP_ERR_INVALID for an unknown key. */
 int isp_set_option(const char* key, int value);
 

@@ -15,7 +15,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 SO_PATH = os.path.join(PKG_DIR, "libisp_tts_b200.so")
-SOURCES = ["isp_capi.cu", "isp_mas.cu", "isp_mas2.cu", "isp_mas_wide.cu", "isp_loglik.cu", "isp_loglik_bwd.cu", "isp_loglik_wide.cu", "isp_consumers.cu", "isp_stage.cu", "isp_ctc.cu", "isp_gemm.cu", "isp_stacks.cu"]
+SOURCES = ["isp_capi.cu", "isp_mas.cu", "isp_mas2.cu", "isp_mas_wide.cu", "isp_mas_cluster.cu", "isp_loglik.cu", "isp_loglik_bwd.cu", "isp_loglik_wide.cu", "isp_consumers.cu", "isp_stage.cu", "isp_ctc.cu", "isp_gemm.cu", "isp_stacks.cu"]
 HEADERS = ["common.cuh", "isp_internal.h", "isp_mas_ptx.cuh", "isp_tc05.cuh", os.path.join("..", "..", "include", "isp_tts_b200.h")]
 
 NVCC_FLAGS = [

@@ -36,6 +36,13 @@ size_t mas_wide_workspace_bytes(int B, int T1max, int T2max);
 int    mas_wide_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text_len, const int64_t* mel_len, int B, int T1max,
                         int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, cudaStream_t stream);
 
+// cluster kernel for long / wide utterances (isp_mas_cluster.cu): T2max <= 1024, one thread-block cluster per utterance
+bool   mas_cluster_supported(int B, int T1max, int T2max);
+size_t mas_cluster_workspace_bytes(int B, int T1max, int T2max);
+int    mas_cluster_set_option(const char* key, int value, int* prev);
+int    mas_cluster_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text_len, const int64_t* mel_len, int B, int T1max,
+                           int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, cudaStream_t stream);
+
 size_t loglik_workspace_bytes(int B, int T1max, int T2max, int D, int dtype);
 int    loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_len, const int64_t* mel_len,
                       int B, int T1max, int T2max, int D, float scale, int attention_prior,

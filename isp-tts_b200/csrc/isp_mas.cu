@@ -725,7 +725,8 @@ static int g_opt_dbg = 0;
 static int g_opt_bits_global = 0;
 static int g_opt_no_tma = 0;
 static int g_opt_cols = 0;     // accepted for compatibility with older tools; the kernel has one strip width
-static int g_opt_impl = 0;     // 0: isp_mas2.cu where it covers the shape, 1: always this file's kernel, 2: isp_mas2.cu or fail, 3: isp_mas_wide.cu
+static int g_opt_impl = 0;     // 0: isp_mas2.cu where it covers the shape, else isp_mas_cluster.cu, else this file's kernel, else isp_mas_wide.cu;
+                               // 1: always this file's kernel, 2: isp_mas2.cu or fail, 3: isp_mas_wide.cu, 4: isp_mas_cluster.cu or fail
 
 int mas_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas.ring_rows")) { *prev = g_opt_ring_rows; g_opt_ring_rows = value; return 0; }
@@ -735,6 +736,7 @@ int mas_set_option(const char* key, int value, int* prev) {
     if (!strcmp(key, "mas.no_tma")) { *prev = g_opt_no_tma; g_opt_no_tma = value; return 0; }
     if (!strcmp(key, "mas.cols_per_lane")) { *prev = g_opt_cols; g_opt_cols = value; return 0; }
     if (!strcmp(key, "mas.impl")) { *prev = g_opt_impl; g_opt_impl = value; return 0; }
+    if (mas_cluster_set_option(key, value, prev) == 0) return 0;
     return mas2_set_option(key, value, prev);
 }
 
@@ -848,12 +850,12 @@ static bool make_maps(MasMaps* maps, const float* logp, int64_t sB, int64_t sT1,
 
 size_t mas_workspace_bytes(int B, int T1max, int T2max) {
     if (B <= 0 || T1max <= 0 || T2max <= 0) return 0;
-    if (T2max > ISP_MAS_MAX_T2) return mas_wide_workspace_bytes(B, T1max, T2max);      // the general kernel (isp_mas_wide.cu)
+    if (T2max > ISP_MAS_MAX_T2) return std::max(mas_wide_workspace_bytes(B, T1max, T2max), mas_cluster_workspace_bytes(B, T1max, T2max));   // isp_mas_cluster.cu / isp_mas_wide.cu
     const int ns = (T2max + kW - 1) / kW;
     const size_t v1 = 256 + size_t(B) * bits_words_for(T1max, ns) * 4 + ((size_t(B) * T1max * 2 + 15) & ~size_t(15));
     const size_t v2 = mas2_workspace_bytes(B);
     const size_t v3 = mas_wide_workspace_bytes(B, T1max, T2max);     // "mas.impl" = 3 runs the general kernel on any shape (tests)
-    return std::max(v1, std::max(v2, v3));
+    return std::max(std::max(v1, mas_cluster_workspace_bytes(B, T1max, T2max)), std::max(v2, v3));
 }
 
 template <bool BS, bool MULTI>
@@ -894,10 +896,20 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
         set_error("isp_mas_forward: workspace too small or not 16 B aligned (%zu < %zu)", ws_bytes, mas_workspace_bytes(B, T1max, T2max));
         return ISP_ERR_WORKSPACE;
     }
+    if (g_opt_impl == 4) {                               // forced (tests): the cluster kernel on any shape it covers
+        if (!mas_cluster_supported(B, T1max, T2max)) { set_error("isp_mas_forward: mas.impl=4 but T1max=%d T2max=%d is outside isp_mas_cluster.cu's range", T1max, T2max); return ISP_ERR_UNSUPPORTED; }
+        return mas_cluster_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws, stream);
+    }
+    const bool want2 = g_opt_impl == 0 || g_opt_impl == 2;
+    const bool fits2 = want2 && !g_opt_bits_global && g_opt_slots != 3 && T2max <= ISP_MAS_MAX_T2 && mas2_supported(B, T1max, T2max);
+    // 641 .. 1024 tokens: one thread-block cluster per utterance (isp_mas_cluster.cu), ~10x the general kernel.  Up to 640 tokens this
+    // file's single-CTA strip kernel is as fast or faster (cfg4, 16 x 4096 x 512: 254 us against ~300 us, tools/masc_compare.py)
+    // and does not need B x T2max / 128 co-resident CTAs, so it keeps that range.
+    if (g_opt_impl == 0 && T2max > ISP_MAS_MAX_T2 && mas_cluster_supported(B, T1max, T2max))
+        return mas_cluster_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws, stream);
     if (T2max > ISP_MAS_MAX_T2 || g_opt_impl == 3)       // wider than the strip kernels: the general kernel (or forced, for tests)
         return mas_wide_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws, stream);
-    const bool want2 = g_opt_impl != 1 && !g_opt_bits_global && g_opt_slots != 3;
-    if (want2 && mas2_supported(B, T1max, T2max))
+    if (fits2)
         return mas2_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws,
                             g_opt_no_tma, g_opt_ring_rows, g_opt_slots, g_opt_dbg, stream, ready, ready_need);
     if (g_opt_impl == 2) { set_error("isp_mas_forward: mas.impl=2 but T1max=%d T2max=%d is outside isp_mas2.cu's range", T1max, T2max); return ISP_ERR_UNSUPPORTED; }

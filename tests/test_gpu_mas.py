@@ -46,7 +46,8 @@ MODES = {"auto": {}, "unpaced_pairs": {"mas2.pace": 0, "mas.slots": 2}, "no_tma"
          "pairs_in_turn": {"mas.slots": 2, "mas2.min_pair_stages": 64}, "two_slots_no_tma": {"mas.slots": 2, "mas.no_tma": 1},
          "v1": {"mas.impl": 1}, "v1_three_slots": {"mas.impl": 1, "mas.slots": 3}, "v1_bits_global": {"mas.impl": 1, "mas.bits_global": 1},
          "v1_two_slots_global_no_tma": {"mas.impl": 1, "mas.slots": 2, "mas.bits_global": 1, "mas.no_tma": 1},
-         "wide": {"mas.impl": 3}}          # isp_mas_wide.cu, the general kernel behind T2max > 640, forced onto every shape
+         "wide": {"mas.impl": 3},          # isp_mas_wide.cu, the general kernel behind T2max > 1024, forced onto every shape
+         "cluster": {"mas.impl": 4}}       # isp_mas_cluster.cu, one thread-block cluster per utterance (641 .. 1024 tokens), forced onto every shape
 
 
 def set_mode(mode):
@@ -152,7 +153,7 @@ def test_maximum_width(cuda_device):
     hard, dur, _ = run_cuda(x, tl, ml, cuda_device)       # text longer than mel: pure diagonal tail
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
     assert_same(hard, dur, rh, rd, "T2=640")
-    # one token more: the general kernel (isp_mas_wide.cu) takes over, same answers
+    # one token more: the cluster kernel (isp_mas_cluster.cu) takes over, same answers
     x = synth.noise_logits(2, 300, 641, 12, quantize=0.5)
     tl, ml = np.array([641, 450]), np.array([300, 211])
     hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
@@ -164,7 +165,7 @@ def test_maximum_width(cuda_device):
 
 @pytest.mark.parametrize("shape", [(3, 900, 1000), (2, 2500, 2100), (2, 700, 4097), (1, 5000, 1024)])
 def test_wide_utterances_general_kernel(cuda_device, shape):
-    """T2max > 640 (long-form text): isp_mas_wide.cu against the oracle, ragged, with ties, path and durations bit-exact,
+    """T2max > 640 (long-form text): isp_mas_cluster.cu up to 1024 tokens, isp_mas_wide.cu beyond, against the oracle, ragged, with ties, path and durations bit-exact,
     also through the path-only entry point."""
     B, T1, T2 = shape
     x = synth.noise_logits(B, T1, T2, 77 + T2, quantize=0.25)
@@ -387,7 +388,32 @@ def test_realistic_logits_against_oracle(cuda_device, name):
     assert np.array_equal(dur.cpu().numpy().sum(1), ml)
 
 
-@pytest.mark.parametrize("mode", ["auto", "two_slots", "v1"])
+@pytest.mark.parametrize("shape", [(4, 1500, 384), (2, 3000, 513), (2, 4096, 1024), (3, 700, 260), (5, 37, 1000), (2, 8000, 300)])
+def test_cluster_kernel_shapes(cuda_device, shape):
+    """isp_mas_cluster.cu (one thread-block cluster per utterance, 1 .. 8 CTAs of 128 tokens): what isp_mas_forward picks for
+    641 .. 1024 tokens, forced here onto narrower shapes too.  Ragged with ties; full-length, tiny and token-heavy utterances in the same batch (clusters whose right
+    CTAs idle, paths that cannot reach column 0); odd T2max takes the loader's register path; path-only entry point too."""
+    B, T1, T2 = shape
+    if T2 <= 640:
+        _lib.set_option("mas.impl", 4)
+    x = synth.noise_logits(B, T1, T2, 177 + T2, quantize=0.25)
+    tl, ml = synth.lengths(B, T2, T1, True, 178 + T2)
+    tl[0], ml[0] = T2, T1
+    tl[1], ml[1] = min(T2, T1 + 40), max(1, min(T1, T2 - 60))     # more tokens than frames: the pure diagonal
+    if B > 2:
+        tl[2], ml[2] = 3, min(T1, 17)                             # an utterance that lives in the first CTA only
+    hard, dur, xt = run_cuda(x, tl, ml, cuda_device)
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard, dur, rh, rd, f"cluster {shape}")
+    _, dur2, path = mas_forward(xt, torch.from_numpy(tl), torch.from_numpy(ml), return_path=True, dense=False)
+    assert np.array_equal(dur2.cpu().numpy(), rd)
+    ref_path = omas.path_from_hard(rh, ml)
+    got = path.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(got[b, :ml[b]], ref_path[b, :ml[b]]) and np.all(got[b, ml[b]:] == -1)
+
+
+@pytest.mark.parametrize("mode", ["auto", "two_slots", "v1", "cluster"])
 def test_all_plateau_adversarial(cuda_device, mode):
     """Every valid cell on the prior's floor (one constant): every comparison of the DP is a tie, so the tie rule alone
     decides the path (surplus frames go to the FIRST token); then the same with one better column."""
