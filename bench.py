@@ -771,6 +771,24 @@ def run_ours(args, w):
                                                  "value": la.item(), "grad_max_rel_diff_vs_torch_fp32": gerr}
         del logits_b, xa, xb2
 
+        # ---- the same step at the reference's own precision outside autocast: fp32 operands, true-fp32 products ----
+        try:
+            from isp_tts_b200.alignment import _align_cuda as _al
+            q32, k32 = q_dev.float(), k_dev.float()
+            t_tf32 = graph_ms(torch, lambda: _al(q32, k32, tl_dev, ml_dev, scale, True, precision="tf32"))
+            t_fp32 = graph_ms(torch, lambda: _al(q32, k32, tl_dev, ml_dev, scale, True, precision="fp32"))
+            l_t = _al(q32, k32, tl_dev, ml_dev, scale, True, precision="tf32")[1]
+            l_f = _al(q32, k32, tl_dev, ml_dev, scale, True, precision="fp32")[1]
+            bwd["precision rows (same workload, fp32 operands)"] = {
+                "fp32_faithful_3xtf32_ms": t_fp32, "fp32_faithful_utt_per_s": B / t_fp32 * 1e3,
+                "tf32_fused_ms": t_tf32, "tf32_fused_utt_per_s": B / t_tf32 * 1e3,
+                "max_abs_diff_logits_tf32_vs_fp32": float((l_t - l_f).abs().max()),
+                "what": "isp_split_3xtf32 x2 + isp_gemm_batched (TF32 over 3 D) + isp_loglik_rows + isp_mas_forward  vs  isp_align_forward on fp32 "
+                        "operands (one TF32 product per term); the headline above is BASELINE configs[2]'s bf16 GEMM"}
+            del q32, k32, l_t, l_f
+        except Exception as exc:                                # pragma: no cover
+            bwd["precision rows (same workload, fp32 operands)"] = {"unsupported": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

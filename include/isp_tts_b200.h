@@ -221,6 +221,12 @@ int    isp_loglik_forward(const void* Q, const void* K, int dtype,
  * above ISP_LOGLIK_MAX_D): S (B, T1max, T2max; row stride ldS) are the UNscaled scores Q.K^T from isp_gemm_batched; the call
  * does alignment.py:190-208 on them (scale, log_softmax over all T2max columns + log prior, masked softmax) one warp per frame
  * row.  Slower than the fused kernel (the scores make a round trip through HBM), same results within the same tolerance. */
+/* Faithful fp32 products on the tensor cores ("3xTF32"): the reference's torch.matmul (alignment.py:189) runs true fp32
+ * (allow_tf32 is off by default), while one kind::tf32 product keeps 10 mantissa bits.  x (rows, D) fp32 -> out (rows, 3 D):
+ * role 0 (frames / Q side) [hi | hi | lo], role 1 (tokens / K side) [hi | lo | hi] with hi = tf32(x), lo = tf32(x - hi), so that
+ * ONE TF32 contraction over 3 D (isp_gemm_batched) gives hi.hi' + hi.lo' + lo.hi' = the fp32 product to ~2^-21; isp_loglik_rows
+ * then does the epilogue.  (What ConvAttention runs outside autocast; gemm_dtype = "tf32" selects the fused single-pass kernel.) */
+int    isp_split_3xtf32(const float* x, int64_t rows, int D, int role, float* out, void* stream);
 int    isp_loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                        float scale, int attention_prior, float* attn_logits, float* attn_soft, void* stream);
 

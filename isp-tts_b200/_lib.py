@@ -20,7 +20,7 @@ ISP_ALIGN_WS_CLEAN = 1
 EXPORTS = [
     "isp_version", "isp_last_error", "isp_device_check",
     "isp_mas_workspace_bytes", "isp_mas_forward", "isp_mas_forward_path", "isp_bin_loss_sums", "isp_length_regulate", "isp_length_regulate_backward", "isp_path_from_durations", "isp_temporal_average", "isp_ctc_workspace_bytes", "isp_ctc_forward", "isp_ctc_backward", "isp_mas_status",
-    "isp_align_workspace_bytes", "isp_align_forward", "isp_loglik_supported", "isp_stage_operands", "isp_unpack_workspace_bytes", "isp_unpack_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_loglik_rows", "isp_loglik_backward_ds", "isp_loglik_backward_from_logits", "isp_gemm_batched", "isp_prep_channels_last", "isp_instance_norm_apply", "isp_soft_average_workspace_bytes", "isp_soft_average", "isp_soft_average_backward", "isp_set_option",
+    "isp_align_workspace_bytes", "isp_align_forward", "isp_loglik_supported", "isp_stage_operands", "isp_unpack_workspace_bytes", "isp_unpack_operands", "isp_loglik_workspace_bytes", "isp_loglik_forward", "isp_split_3xtf32", "isp_loglik_rows", "isp_loglik_backward_ds", "isp_loglik_backward_from_logits", "isp_gemm_batched", "isp_prep_channels_last", "isp_instance_norm_apply", "isp_soft_average_workspace_bytes", "isp_soft_average", "isp_soft_average_backward", "isp_set_option",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def load():
     lib.isp_loglik_workspace_bytes.restype = c_sz
     lib.isp_loglik_forward.argtypes = [vp, vp, c_int, vp, vp, c_int, c_int, c_int, c_int, f32, c_int, vp, vp, vp, c_sz, vp]
     lib.isp_loglik_forward.restype = c_int
+    lib.isp_split_3xtf32.argtypes = [vp, c_i64, c_int, c_int, vp, vp]
+    lib.isp_split_3xtf32.restype = c_int
     lib.isp_loglik_rows.argtypes = [vp, c_i64, vp, vp, c_int, c_int, c_int, f32, c_int, vp, vp, vp]
     lib.isp_loglik_rows.restype = c_int
     lib.isp_loglik_backward_ds.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, f32, c_int, vp, c_int, vp]

@@ -156,9 +156,29 @@ def batch_diagonal_prior(text_lengths: Tensor, mel_lengths: Tensor, gamma: float
     return prior.masked_fill(prior < threshold, 0.0)
 
 
-def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool, want_rowsum: bool = False):
+def _split_3xtf32(x: Tensor, role: int) -> Tensor:
+    """(B, T, D) fp32 -> (B, T, 3 D): [hi | hi | lo] for frames (role 0), [hi | lo | hi] for tokens (role 1) (isp_split_3xtf32)."""
+    lib = _lib.load()
+    B, T, D = x.shape
+    out = torch.empty((B, T, 3 * D), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.isp_split_3xtf32(x.data_ptr(), B * T, D, role, out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "isp_split_3xtf32")
+    return out
+
+
+def _scores_fp32(q: Tensor, k: Tensor, text_len: Tensor | None, mel_len: Tensor | None) -> Tensor:
+    """S = Q.K^T with fp32-faithful products on the tensor cores: the three TF32 partial products hi.hi' + hi.lo' + lo.hi' as one
+    contraction over 3 D (what the reference's torch.matmul computes in true fp32, alignment.py:189)."""
+    return bgemm(_split_3xtf32(q.contiguous(), 0), _split_3xtf32(k.contiguous(), 1).transpose(1, 2), m_len=mel_len, n_len=text_len)
+
+
+def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool, want_rowsum: bool = False,
+                 precision: str = "tf32"):
     """(attn_soft, attn_logits) -- and, with want_rowsum, the prior's row sums (B, T1) the fused kernel leaves for the backward
-    pass (None when the shape went through the stand-alone row epilogue)."""
+    pass (None when the shape went through the stand-alone row epilogue).  precision (fp32 operands only): "tf32" = one
+    tensor-core product per term inside the fused kernel (10-bit mantissa), "fp32" = the 3xTF32 split (_scores_fp32) followed by
+    the stand-alone row epilogue: the reference's own precision, ~3x the GEMM work and a round trip of the scores through HBM."""
     dev = q.device
     _lib.require_device(dev)
     lib = _lib.load()
@@ -175,10 +195,12 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
     logits = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
     soft = torch.empty((B, T1, T2), dtype=torch.float32, device=dev)
     dt = _lib.ISP_DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
-    if not lib.isp_loglik_supported(T2, D, dt):
-        # outside the fused kernel's range (long-form text, odd attention_dim, fp32 operands too wide for shared memory): scores from the batched GEMM, then the
-        # stand-alone row epilogue (isp_loglik_rows) -- slower by the scores' round trip through HBM, same results
-        s = bgemm(q, k.transpose(1, 2), m_len=ml, n_len=tl)
+    faithful = precision == "fp32" and q.dtype == torch.float32
+    if faithful or not lib.isp_loglik_supported(T2, D, dt):
+        # outside the fused kernel's range (long-form text, odd attention_dim, fp32 operands too wide for shared memory), or fp32-faithful
+        # products asked for: scores from the batched GEMM, then the stand-alone row epilogue (isp_loglik_rows) -- slower by the
+        # scores' round trip through HBM
+        s = _scores_fp32(q, k, tl, ml) if faithful and D % 4 == 0 else bgemm(q, k.transpose(1, 2), m_len=ml, n_len=tl)
         with torch.cuda.device(dev):
             rc = lib.isp_loglik_rows(s.data_ptr(), s.stride(1), tl.data_ptr(), ml.data_ptr(), B, T1, T2, float(scale),
                                      1 if prior else 0, logits.data_ptr(), soft.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
@@ -195,7 +217,7 @@ def _loglik_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale:
 
 
 def _align_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float, prior: bool, return_path: bool = False,
-                dense: bool = True, want_rowsum: bool = False):
+                dense: bool = True, want_rowsum: bool = False, precision: str = "tf32"):
     """isp_align_forward: the log-likelihood kernel and the MAS kernel linked through per-utterance ready counts (the second
     starts under the first's last wave).  Returns (soft, logits, hard, durations, path) -- and the prior's row sums for the
     backward pass with want_rowsum (None when the fused log-likelihood kernel does not cover the shape)."""
@@ -211,8 +233,8 @@ def _align_cuda(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: 
     if not dense and not return_path:
         raise ValueError("dense=False needs return_path=True")
     dt = _lib.ISP_DTYPE_BF16 if q.dtype == torch.bfloat16 else _lib.ISP_DTYPE_F32
-    if not lib.isp_loglik_supported(T2, D, dt):
-        soft, logits = _loglik_cuda(q, k, text_len, mel_len, scale, prior)
+    if (precision == "fp32" and q.dtype == torch.float32) or not lib.isp_loglik_supported(T2, D, dt):
+        soft, logits = _loglik_cuda(q, k, text_len, mel_len, scale, prior, precision=precision)
         out = mas_forward(logits, text_len, mel_len, durations=True, return_path=return_path, dense=dense)
         res = (soft, logits, out[0], out[1], (out[2] if return_path else None))
         return res + (None,) if want_rowsum else res
@@ -412,13 +434,14 @@ class _LogLikelihood(torch.autograd.Function):
     nothing is lost); every row of dQ / dK is computed, padded ones included, exactly as autograd would."""
 
     @staticmethod
-    def forward(ctx, q, k, text_len, mel_len, scale, prior, with_mas=False):
-        ctx.scale, ctx.prior, ctx.with_mas = scale, prior, with_mas
+    def forward(ctx, q, k, text_len, mel_len, scale, prior, with_mas=False, precision="tf32"):
+        ctx.scale, ctx.prior, ctx.with_mas, ctx.precision = scale, prior, with_mas, precision
         if with_mas:
             # the linked call (isp_align_forward): the hard path and the durations come with it, outside autograd
-            soft, logits, hard, dur, _, rowsum = _align_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior, want_rowsum=True)
+            soft, logits, hard, dur, _, rowsum = _align_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior, want_rowsum=True,
+                                                             precision=precision)
         else:
-            soft, logits, rowsum = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior, want_rowsum=True)
+            soft, logits, rowsum = _loglik_cuda(q.detach(), k.detach(), text_len, mel_len, scale, prior, want_rowsum=True, precision=precision)
         # The backward pass works from attn_logits and the prior's row sums when the fused kernel produced them (no score GEMM, no
         # attn_soft read); otherwise (stand-alone row epilogue, token axis not a multiple of 4) from recomputed scores and attn_soft.
         ctx.from_logits = rowsum is not None and logits.shape[2] % 4 == 0
@@ -435,32 +458,36 @@ class _LogLikelihood(torch.autograd.Function):
     def backward(ctx, g_soft, g_logits, *_):
         q, k, saved, rowsum, text_len, mel_len = ctx.saved_tensors
         if g_soft is None and g_logits is None:
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         qd, kd = q.detach().contiguous(), k.detach().contiguous()
         if ctx.from_logits:
             d_s = loglik_backward_from_logits(saved, g_logits, g_soft, rowsum, text_len, mel_len, ctx.scale, ctx.prior, out_dtype=q.dtype)
         else:
-            d_s = loglik_backward_ds(_scores(qd, kd, text_len, mel_len), saved, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
+            faithful = ctx.precision == "fp32" and qd.dtype == torch.float32 and qd.shape[2] % 4 == 0
+            sc = _scores_fp32(qd, kd, text_len, mel_len) if faithful else _scores(qd, kd, text_len, mel_len)
+            d_s = loglik_backward_ds(sc, saved, g_logits, g_soft, ctx.scale, ctx.prior, out_dtype=q.dtype)
         gq = bgemm(d_s, kd, out_dtype=q.dtype, k_len=text_len) if ctx.needs_input_grad[0] else None
         gk = bgemm(d_s.transpose(1, 2), qd, out_dtype=k.dtype, k_len=mel_len) if ctx.needs_input_grad[1] else None
-        return gq, gk, None, None, None, None, None
+        return gq, gk, None, None, None, None, None, None
 
 
 def align_forward(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float | None = None,
-                  attention_prior: bool = True):
+                  attention_prior: bool = True, precision: str = "tf32"):
     """The whole hot path in one linked call (isp_align_forward): (attn_soft, attn_logits, attn_hard int16, durations int64)
     from encoded frames q (B, T1, D) and tokens k (B, T2, D).  attn_soft and attn_logits carry gradients to q and k exactly as
     loglik_forward's do; the hard path and the durations are outside autograd (alignment.py:291 torch.no_grad)."""
     scale = q.shape[-1] ** -0.5 if scale is None else scale
-    return _LogLikelihood.apply(q, k, text_len, mel_len, scale, attention_prior, True)
+    return _LogLikelihood.apply(q, k, text_len, mel_len, scale, attention_prior, True, precision)
 
 
 def loglik_forward(q: Tensor, k: Tensor, text_len: Tensor, mel_len: Tensor, scale: float | None = None,
-                   attention_prior: bool = True):
+                   attention_prior: bool = True, precision: str = "tf32"):
     """(attn_soft, attn_logits) from encoded frames q (B, T1, D) and tokens k (B, T2, D);
-    rows of q / k past each utterance's length must be zero (the projections guarantee it)."""
+    rows of q / k past each utterance's length must be zero (the projections guarantee it).
+    precision, for float32 operands: "tf32" (the fused kernel, one tensor-core product per term) or "fp32" (3xTF32 split: the
+    reference's own precision; bfloat16 operands ignore it)."""
     scale = q.shape[-1] ** -0.5 if scale is None else scale
-    return _LogLikelihood.apply(q, k, text_len, mel_len, scale, attention_prior)
+    return _LogLikelihood.apply(q, k, text_len, mel_len, scale, attention_prior, False, precision)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -528,8 +555,10 @@ class ConvAttention(nn.Module, _ConfigInit):
         self.mel_dim, self.text_dim = mel_dim, text_dim
         self.scale = attention_dim ** -0.5
         self.attention_prior = attention_prior
-        #: "auto": bf16 operands under autocast, else "fp32" = fp32 operands in memory with TF32 tensor-core products (10-bit
-        #: mantissa, fp32 accumulate: within 1e-3 relative of the fp32 reference, tests/test_gpu_loglik.py); or "bf16"
+        #: "auto": bf16 operands under autocast, else "fp32" = what the reference computes outside autocast (torch.matmul in true
+        #: fp32, alignment.py:189): fp32 operands, products as the 3xTF32 split on the tensor cores (within ~1e-6 of fp32), the
+        #: epilogue as a stand-alone kernel.  "tf32": fp32 operands in memory, ONE tensor-core product per term inside the fused
+        #: kernel (10-bit mantissa, fp32 accumulate: within 1e-3 relative of the fp32 reference, ~2x faster than "fp32").  "bf16".
         self.gemm_dtype = "auto"
         #: projection stacks on the sm_100a kernels (stacks.py) when no gradient is needed: "auto" = in bf16 mode (autocast,
         #: the recipe's mixed-precision setting) -- in fp32 mode the torch ops run, because TF32 products through two
@@ -602,7 +631,10 @@ class ConvAttention(nn.Module, _ConfigInit):
         """queries (B, mel_dim, T1) mel, keys (B, text_dim, T2) encoded text, lengths (B,)
         -> (attn_soft, attn_logits), both (B, T1, T2) fp32 (alignment.py:159-208)."""
         q, k = self._operands(queries, keys, query_len, key_len)
-        return loglik_forward(q, k, key_len, query_len, self.scale, self.attention_prior)
+        return loglik_forward(q, k, key_len, query_len, self.scale, self.attention_prior, precision=self._precision())
+
+    def _precision(self) -> str:
+        return "tf32" if self._mode() == "tf32" else "fp32"
 
     def _operands(self, queries: Tensor, keys: Tensor, query_len: Tensor, key_len: Tensor):
         q, k = self.encode(queries, keys, query_len, key_len)
@@ -614,7 +646,7 @@ class ConvAttention(nn.Module, _ConfigInit):
         """forward() plus the MAS hard path and the durations from the same linked call (align_forward):
         (attn_soft, attn_logits, attn_hard, durations)."""
         q, k = self._operands(queries, keys, query_len, key_len)
-        return align_forward(q, k, key_len, query_len, self.scale, self.attention_prior)
+        return align_forward(q, k, key_len, query_len, self.scale, self.attention_prior, precision=self._precision())
 
 
 class AlignerOutput(NamedTuple):

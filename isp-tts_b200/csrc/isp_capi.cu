@@ -141,6 +141,9 @@ int isp_loglik_forward(const void* Q, const void* K, int dtype, const int64_t* t
                                attn_logits, attn_soft, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int isp_split_3xtf32(const float* x, int64_t rows, int D, int role, float* out, void* stream) {
+    return isp::split_3xtf32(x, rows, D, role, out, static_cast<cudaStream_t>(stream));
+}
 int isp_loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                     float scale, int attention_prior, float* attn_logits, float* attn_soft, void* stream) {
     return isp::loglik_rows(S, ldS, text_len, mel_len, B, T1max, T2max, scale, attention_prior, attn_logits, attn_soft, static_cast<cudaStream_t>(stream));

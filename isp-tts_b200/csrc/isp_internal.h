@@ -51,6 +51,7 @@ bool   loglik_supported(int T2max, int D, int dtype);
 int    loglik_tiles_per_utterance(int T1max);     // what `ready[b]` reaches when utterance b's outputs are complete
 int    loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                    float scale, int attention_prior, float* attn_logits, float* attn_soft, cudaStream_t stream);
+int    split_3xtf32(const float* x, int64_t rows, int D, int role, float* out, cudaStream_t stream);
 int    loglik_set_option(const char* key, int value, int* prev);
 int    loglik_backward_ds(const float* S, const float* attn_soft, const float* g_logits, const float* g_soft,
                           int B, int T1max, int T2max, float scale, int attention_prior, void* dS, int ds_dtype, cudaStream_t stream);

@@ -87,7 +87,40 @@ loglik_rows_kernel(const float* __restrict__ S, const int64_t* __restrict__ text
     }
 }
 
+// x = hi + lo with hi = x rounded to TF32 (10-bit mantissa) and lo = the rounded remainder: hi*hi' + hi*lo' + lo*hi' reproduces the
+// fp32 product to ~2^-21 (the dropped lo*lo' term is 2^-22 relative), which the tensor cores accumulate in fp32.  The three terms
+// become ONE contraction over 3 D: the frame side is laid out [hi | hi | lo], the token side [hi | lo | hi].
+__global__ void __launch_bounds__(256)
+split_3xtf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int D, int role) {
+    const long long total = rows * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / D;
+        const int d = int(i - r * D);
+        const float v = x[i];
+        uint32_t hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        const float hi = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+        const float lo = __uint_as_float(lb);
+        float* o = out + r * 3 * D + d;
+        o[0] = hi;
+        o[D] = role == 0 ? hi : lo;
+        o[2 * D] = role == 0 ? lo : hi;
+    }
+}
+
 }  // namespace
+
+int split_3xtf32(const float* x, int64_t rows, int D, int role, float* out, cudaStream_t stream) {
+    if (!x || !out) { set_error("isp_split_3xtf32: null pointer"); return ISP_ERR_INVALID; }
+    if (rows <= 0 || D <= 0 || (role != 0 && role != 1)) { set_error("isp_split_3xtf32: rows and D must be positive, role 0 (frames) or 1 (tokens)"); return ISP_ERR_INVALID; }
+    const long long total = (long long)rows * D;
+    const int grid = int(std::min<long long>((total + 255) / 256, 148LL * 16));
+    split_3xtf32_kernel<<<grid, 256, 0, stream>>>(x, out, rows, D, role);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "split_3xtf32_kernel launch");
+    return 0;
+}
 
 int loglik_rows(const float* S, int64_t ldS, const int64_t* text_len, const int64_t* mel_len, int B, int T1max, int T2max,
                 float scale, int attention_prior, float* attn_logits, float* attn_soft, cudaStream_t stream) {

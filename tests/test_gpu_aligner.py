@@ -19,10 +19,13 @@ def build(g, dev):
     return al.to(dev)
 
 
+@pytest.mark.parametrize("mode", ["auto", "tf32"])
 @pytest.mark.parametrize("tag", ["small", "dim80", "dim128"])
-def test_forward_matches_reference(cuda_device, tag):
+def test_forward_matches_reference(cuda_device, tag, mode):
+    """mode "auto" outside autocast = the reference's fp32 products (3xTF32 split); "tf32" = the fused single-pass kernel."""
     g = golden(f"loglik_{tag}.npz")
     al = build(g, cuda_device)
+    al.attention.gemm_dtype = mode
     mel = torch.from_numpy(g["mel"]).to(cuda_device)
     txt = torch.from_numpy(g["enc_text"]).to(cuda_device)
     ml = torch.from_numpy(g["mel_len"]).to(cuda_device)
@@ -36,6 +39,8 @@ def test_forward_matches_reference(cuda_device, tag):
     _, _, parts = oll.loglik(g["Q"], g["K"], g["text_len"], g["mel_len"], return_parts=True)
     ok = ~oll.threshold_ambiguous(parts["prior_raw"])
     err = np.abs(logits - g["attn_logits"])
+    # (both modes: the projection stacks in front are torch / cuDNN convolutions, TF32 by torch's default exactly as in the reference
+    # on a GPU -- the golden comes from a CPU run; tests/test_gpu_loglik.py::test_fp32_faithful_products bounds the contraction itself)
     assert np.all(err[ok] <= 1e-3 * np.abs(g["attn_logits"][ok]) + 1e-4), err[ok].max()
     # MAS is bit-exact GIVEN the logits: oracle on OUR logits == our path
     rh, rd = omas.b_mas_with_durations(logits, g["text_len"], g["mel_len"])

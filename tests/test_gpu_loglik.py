@@ -78,6 +78,35 @@ def test_golden_reference_outputs(cuda_device, tag, dtype):
     assert np.allclose(soft.sum(2)[rows], 1.0, atol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(6, 300, 100, 128), (5, 130, 201, 80), (3, 700, 256, 128), (2, 129, 8, 16), (2, 200, 600, 64)])
+def test_fp32_faithful_products(cuda_device, shape):
+    """precision="fp32": the 3xTF32 split (isp_split_3xtf32 + one TF32 contraction over 3 D + isp_loglik_rows) -- what the
+    drop-in runs outside autocast, where the reference's matmul is true fp32.  Scores within 2e-6 of |Q||K| against float64
+    (one TF32 product: ~5e-4), attn_logits within 2e-5 relative + 2e-5 of the oracle, 50x tighter than the TF32 tolerance;
+    gradients flow through the same precision."""
+    B, T1, T2, D = shape
+    tl, ml = synth.lengths(B, T2, T1, True, 77 + T2)
+    q, k = synth.encoded_pair(B, T1, T2, D, tl, ml, 99 + T1)
+    dev = cuda_device
+    qt, kt = torch.from_numpy(q).to(dev), torch.from_numpy(k).to(dev)
+    from isp_tts_b200.alignment import _scores_fp32, _scores
+    s3 = _scores_fp32(qt, kt, None, None).cpu().numpy().astype(np.float64)
+    s1 = _scores(qt, kt).cpu().numpy().astype(np.float64)
+    ref = q.astype(np.float64) @ k.astype(np.float64).transpose(0, 2, 1)
+    norm = np.linalg.norm(q.astype(np.float64), axis=2)[:, :, None] * np.linalg.norm(k.astype(np.float64), axis=2)[:, None, :] + 1e-30
+    e3, e1 = float((np.abs(s3 - ref) / norm).max()), float((np.abs(s1 - ref) / norm).max())
+    assert e3 < 2e-6 and e3 < e1 / 20, (e3, e1)
+    qg, kg = qt.clone().requires_grad_(True), kt.clone().requires_grad_(True)
+    soft, logits = loglik_forward(qg, kg, torch.from_numpy(tl).to(dev), torch.from_numpy(ml).to(dev), precision="fp32")
+    rs, rl, parts = oll.loglik(q, k, tl, ml, return_parts=True)
+    amb = oll.threshold_ambiguous(parts["prior_raw"])
+    compare(soft.detach().cpu().numpy(), logits.detach().cpu().numpy(), rs, rl, amb, dict(rel=2e-5, abs=2e-5, soft=2e-5), f"{shape}/fp32 faithful")
+    if T2 > 512:
+        return                                       # (isp_loglik_backward_ds stops at 512 tokens)
+    (soft * soft).sum().backward()
+    assert torch.isfinite(qg.grad).all() and torch.isfinite(kg.grad).all() and float(qg.grad.abs().sum()) > 0
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(6, 300, 100, 128), (5, 130, 201, 80), (3, 700, 256, 128), (2, 129, 8, 16)])
 def test_against_oracle(cuda_device, shape, dtype):
