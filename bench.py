@@ -353,6 +353,27 @@ def run_ours(args, w):
         qp_host, kp_host = pack_rows(q_host, ml).pin_memory(), pack_rows(k_host, tl).pin_memory()
         for bf in bufs:
             bf["qp"], bf["kp"] = torch.empty_like(qp_host, device=dev), torch.empty_like(kp_host, device=dev)
+    arena_host = None
+    if args.e2e_copy == "arena":
+        # the same packed rows and the two length vectors as views of ONE pinned arena (what a collate function that writes into a
+        # pre-pinned buffer produces): one DMA per step, nothing between two steps' transfers on the copy stream; the scatter into
+        # the padded operands runs on the compute stream
+        qp_t, kp_t = pack_rows(q_host, ml), pack_rows(k_host, tl)
+        parts = [("tl", tl_host), ("ml", ml_host), ("qp", qp_t), ("kp", kp_t)]
+        offs, total_b = {}, 0
+        for name, t in parts:
+            offs[name] = total_b
+            total_b += (t.numel() * t.element_size() + 255) // 256 * 256
+        arena_host = torch.empty((total_b,), dtype=torch.uint8).pin_memory()
+
+        def views(arena):
+            return {name: arena[offs[name]: offs[name] + t.numel() * t.element_size()].view(t.dtype).view(t.shape) for name, t in parts}
+        hv = views(arena_host)
+        for name, t in parts:
+            hv[name].copy_(t)
+        for bf in bufs:
+            bf["arena"] = torch.empty((total_b,), dtype=torch.uint8, device=dev)
+            bf.update(views(bf["arena"]))
     dur_hosts = [torch.empty((B, T2), dtype=torch.int64).pin_memory() for _ in range(2)]
     hard_hosts = [torch.empty((B, T1, T2), dtype=torch.int16).pin_memory() for _ in range(2)] if args.e2e_outputs == "hard" else None
     state = {"i": 0}
@@ -361,6 +382,10 @@ def run_ours(args, w):
         bf = bufs[slot]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(bf["free"])                 # the kernels that read this buffer two steps ago are done
+            if args.e2e_copy == "arena":
+                bf["arena"].copy_(arena_host, non_blocking=True)
+                bf["ready"].record(copy_stream)
+                return
             bf["tl"].copy_(tl_host, non_blocking=True)
             bf["ml"].copy_(ml_host, non_blocking=True)
             if args.e2e_copy == "packed":
@@ -385,6 +410,8 @@ def run_ours(args, w):
         bf = bufs[slot]
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(bf["ready"])
+        if args.e2e_copy == "arena":
+            unpack_operands(bf["qp"], bf["kp"], bf["tl"], bf["ml"], T1, T2, out_q=bf["q"], out_k=bf["k"])
         if linked:
             soft, logits, hard, dur, _ = _align_cuda(bf["q"], bf["k"], bf["tl"], bf["ml"], scale, True)
         else:
@@ -499,7 +526,7 @@ def run_ours(args, w):
     e2e_ms = max_over_ranks(s2.elapsed_time(e2))
     # The platform's ceiling for that leg: the same number of bytes per step as ONE plain pinned cudaMemcpyAsync on the copy
     # engine, all ranks at once, nothing else running (what the host side of the PCIe tree gives N GPUs together)
-    ceil_bytes = int((ml.sum() + tl.sum()) * D * q_host.element_size()) if args.e2e_copy in ("staged", "packed") else \
+    ceil_bytes = int((ml.sum() + tl.sum()) * D * q_host.element_size()) if args.e2e_copy in ("staged", "packed", "arena") else \
         q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size()
     flat_host = q_host.view(-1)[: ceil_bytes // q_host.element_size()]
     flat_dev = torch.empty_like(flat_host, device=dev)
@@ -856,7 +883,7 @@ def run_ours(args, w):
 
     utts = global_B * args.steps
     valid_cells = float(global_cells if strong else (tl * ml).sum() * world) * args.steps
-    if args.e2e_copy in ("staged", "packed"):
+    if args.e2e_copy in ("staged", "packed", "arena"):
         h2d = int((ml.sum() + tl.sum()) * D * q_host.element_size()) + 16 * B
     else:
         h2d = q_host.numel() * q_host.element_size() + k_host.numel() * k_host.element_size() + 16 * B
@@ -883,6 +910,8 @@ def run_ours(args, w):
                 "link_ceiling": "aggregate H2D rate of plain pinned cudaMemcpyAsync of the same bytes on all ranks at once, nothing else running",
                 "api": ({"staged": "isp_stage_operands (padded pinned host tensors; valid rows only cross PCIe, zero-copy reads) + ",
                          "packed": "two cudaMemcpyAsync of PACKED pinned host buffers (valid rows back to back) + isp_unpack_operands + ",
+                         "arena": "ONE cudaMemcpyAsync per step of a pinned host arena holding the lengths and the PACKED rows of Q and K (valid rows back to "
+                                  "back, as a collate function that writes into a pre-pinned buffer leaves them) + isp_unpack_operands on the compute stream + ",
                          "padded": ""}[args.e2e_copy])
                        + ("isp_align_forward (the two kernels linked)" if linked else "isp_loglik_forward + isp_mas_forward") + " through isp_tts_b200.  In: pinned host Q, K (already cast to the GEMM's "
                        + ("bf16" if elem == 2 else "fp32") + " on the host, outside the timed region) and int64 lengths.  Out: the int64 durations"
@@ -918,7 +947,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (cfg5 sweep: 64..4096 with the cfg3 length law); 0 = the workload's own")
     ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
                     help="resident-input timing: replay the step as a CUDA graph (default) or launch it through the Python wrappers")
-    ap.add_argument("--e2e-copy", default="packed", choices=["packed", "staged", "padded"],
+    ap.add_argument("--e2e-copy", default="arena", choices=["arena", "packed", "staged", "padded"],
                     help="end-to-end H2D of Q and K: packed rows by DMA + isp_unpack_operands (default), isp_stage_operands (zero-copy reads "
                          "of the valid rows of padded host tensors), or plain copies of the padded tensors")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (sweeps)")
