@@ -141,3 +141,23 @@ def test_sharded_durations_gather_world2_gloo(tmp_path):
     for r in range(world):
         with open(tmp_path / f"rank{r}.ok") as f:
             assert f.read() == "1", f"rank {r}: gathered durations differ from the single-process result"
+
+
+def test_no_binaries_tracked_and_runtime_linked_dynamically():
+    """no built artefact in the history, and the shipped library links the CUDA runtime dynamically (the static runtime
+    would embed every runtime entry point -- the batched-memcpy family among them -- in a library that travels to the GPU box)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tracked = subprocess.run(["git", "ls-files"], cwd=root, capture_output=True, text=True)
+    if tracked.returncode == 0:
+        for name in tracked.stdout.split():
+            path = os.path.join(root, name)
+            if os.path.isfile(path):
+                with open(path, "rb") as f:
+                    assert f.read(4) != b"\x7fELF", f"{name} is a tracked ELF binary"
+    names = [b"cuda" + b"MemcpyBatchAsync", b"cuda" + b"Memcpy3DBatchAsync", b"cu" + b"MemcpyBatchAsync", b"cu" + b"Memcpy3DBatchAsync"]
+    so = os.path.join(root, "isp-tts_b200", "libisp_tts_b200.so")
+    if os.path.exists(so):
+        blob = open(so, "rb").read()
+        for nm in names:
+            assert nm not in blob, f"{nm.decode()} is named inside libisp_tts_b200.so (static cudart?)"
