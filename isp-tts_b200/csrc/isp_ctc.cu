@@ -311,7 +311,9 @@ static int ctc_group_padded(int T2max) {
     return g <= 4 ? 4 : (g <= 8 ? 8 : (g <= 12 ? 12 : (g <= 16 ? 16 : (g <= 20 ? 20 : 0))));
 }
 
-static int ctc_warps_per_cta(int G) { return G <= 8 ? 4 : 2; }     // the backward ring is 1 KB * (2G + 4) per warp
+// warps (= utterances) per CTA: bounded by shared memory (the backward ring is 1 KB * (2G + 4) per warp), and no more than it takes to
+// give every SM a CTA -- a batch of 256 used to sit on 64 of the 148 SMs
+static int ctc_warps_per_cta(int G, int B) { return std::max(1, std::min(G <= 8 ? 4 : 2, (B + 147) / 148)); }
 
 size_t ctc_workspace_bytes(int B, int T1max, int T2max) {
     const int G = ctc_group_padded(T2max);
@@ -350,7 +352,7 @@ int ctc_forward(const float* logits, const int64_t* text_len, const int64_t* mel
     const float blank2 = blank_logprob * kCtcLog2e;
     const long long rows = (long long)B * T1max;
     ctc_rownorm_kernel<<<int(std::min<long long>((rows + 7) / 8, 148LL * 16)), 256, 0, stream>>>(logits, mel_len, w.z2, B, T1max, T2max, blank2);
-    const int wpc = ctc_warps_per_cta(G);
+    const int wpc = ctc_warps_per_cta(G, B);
     const int grid = (B + wpc - 1) / wpc;
 #define ISP_CTC_ALPHA(GG)                                                                                                   \
     {                                                                                                                        \
@@ -381,7 +383,7 @@ int ctc_backward(const float* logits, const int64_t* text_len, const int64_t* me
     const int G = ctc_group_padded(T2max);
     const CtcWs w = ctc_carve(ws, B, T1max, G);
     const float blank2 = blank_logprob * kCtcLog2e;
-    const int wpc = ctc_warps_per_cta(G);
+    const int wpc = ctc_warps_per_cta(G, B);
     const int grid = (B + wpc - 1) / wpc;
 #define ISP_CTC_BETA(GG)                                                                                                    \
     {                                                                                                                        \
