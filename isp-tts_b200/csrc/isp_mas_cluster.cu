@@ -43,9 +43,6 @@
 #include "isp_internal.h"
 #include "isp_mas_ptx.cuh"
 
-#ifndef ISP_MASC_POLL
-#define ISP_MASC_POLL 1         // A/B (tools/ab_build.sh): 1 = a waiting strip sleeps on one slot before it reads its chunk of slots
-#endif
 #ifndef ISP_MASC_PUT_END
 #define ISP_MASC_PUT_END 0      // A/B: 1 = the chunk's boundary stores in one burst after its rounds, 0 = one per round
 #endif
@@ -195,6 +192,12 @@ ISP_DEVINL uint32_t spread16(uint32_t x) {
 }
 ISP_DEVINL uint32_t interleave16(uint32_t e, uint32_t o) { return spread16(e) | (spread16(o) << 1); }
 ISP_DEVINL long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+ISP_DEVINL void sts_u16_(uint32_t sa, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa), "h"(short(v)) : "memory"); }
+ISP_DEVINL int lds_u16_(uint32_t sa) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(sa) : "memory");
+    return int(v);
+}
 ISP_DEVINL void spin_check(uint32_t& spins) { if (++spins > (1u << 25)) __trap(); }   // a protocol bug must not hang the GPU
 
 // =================================== the strip warp: forward DP ===================================================
@@ -209,7 +212,7 @@ ISP_DEVINL void spin_check(uint32_t& spins) { if (++spins > (1u << 25)) __trap()
 // HAS_PREV: a strip on the left feeds this one's column 0; HAS_NEXT: this strip feeds one on the right.
 template <bool HAS_PREV, bool HAS_NEXT>
 ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, int lane, int n, uint32_t rank, long long* tr) {
-    long long w_land = 0, w_bnd = 0;
+    long long w_land = 0, w_bnd = 0;      // trace: cycles spent waiting for logits / for the strip on the left
     const uint32_t ring = smem_sa + p.off_ring + uint32_t(s * kStrip + 2 * lane) * 4u;
     const uint32_t rmask = uint32_t(p.ring_rows - 1);
     const uint32_t bits_sa = smem_sa + p.off_bits + uint32_t(s) * 8u;                     // row r at + 16 r
@@ -231,21 +234,17 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
 
     // Q[r][j] = x[r][j] + max(Q[r-1][j-1], Q[r-1][j]), bit = Q[r-1][j-1] >= Q[r-1][j]   (mas.py:14, :17)
     // rows r = R + 2k and r + 1; bA = Q[r-1][-1], bB = Q[r][-1] of this strip (the strip on the left, or the virtual Q[-1][-1] = 0 / -inf)
-    // pf: address of the even row of the next chunk's logits for this round (0 = none), loaded behind the round's shuffles.
-    // The boundary values (this strip's last column) are NOT stored from inside the rounds: a store reads its registers when it
-    // leaves the memory-instruction queue, so the next round's results could not be written until then (measured: 43 -> 76 cycles
-    // per row, whatever the kind of store).  They are kept in registers of their own and leave at the end of the chunk.
-    // (Each pair of slots is assembled in a register quad of its own, so that the stores need no staging registers: eight stores
-    // through one staging quad wait for one another's operand reads, ~90 cycles apiece.)
+    // pf: address of the even row of the next chunk's logits for this round (0 = none), loaded in front of the round's shuffles;
+    // the round's two boundary values leave as one 16 B store of two {value, tag} slots at its end.  (Measured alternatives, all
+    // slower on cfg4: the loads behind the shuffles, the chunk's stores in one burst after its rounds, the pairs assembled in
+    // register quads of their own, weak / plain shared stores -- DESIGN.md section 4.2.)
     uint4 bq[kCh / 2];
     auto step2 = [&](int R, int k, float2 xa, float2 xb, float ha, float bA, float bB, uint32_t slot, uint32_t pf, float2& na, float2& nb,
                      float& nh) __attribute__((always_inline)) {
+        if (pf) { na = lds_f32x2_(pf); nb = lds_f32x2_(pf + kRowBytes); nh = lds_f32(pf - 4u); }
         const float t1 = __shfl_sync(0xffffffffu, q1, src);
         const float t0 = __shfl_sync(0xffffffffu, q0, src);
-        if (pf) { na = lds_f32x2_(pf); nb = lds_f32x2_(pf + kRowBytes); nh = lds_f32(pf - 4u); }
-#if !ISP_MASC_PUT_END
-        if (HAS_NEXT && k > 0) put4(slot - 16u, bq[k - 1]);          // the previous round's pair, from its own registers, behind the shuffles
-#endif
+
         const float L1 = lane0 ? bA : t1;                    // Q[r-1][2l-1]
         const float hh = __fadd_rn(ha, fmaxf(t0, L1));       // Q[r][2l-1], as its owner computes it
         const float H = lane0 ? bB : hh;
@@ -260,7 +259,11 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
         const bool mine_a = lane == 2 * k, mine_b = lane == 2 * k + 1;
         ke = mine_a ? ea : ke; ko = mine_a ? oa : ko;
         ke = mine_b ? eb : ke; ko = mine_b ? ob : ko;
+#if ISP_MASC_PUT_END
         if (HAS_NEXT) bq[k] = make_uint4(__float_as_uint(n1), uint32_t(R + 2 * k + 1), __float_as_uint(q1), uint32_t(R + 2 * k + 2));
+#else
+        if (HAS_NEXT) st_slot2_if(bnd_out + slot, n1, R + 2 * k + 1, q1, R + 2 * k + 2, lane31);
+#endif
     };
     auto step1 = [&](int r, float2 xa, float bA, uint64_t slot) __attribute__((always_inline)) {
         const float t1 = __shfl_sync(0xffffffffu, q1, src);
@@ -281,16 +284,13 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
             if (tr) w_land += clock64() - t0;
         }
     };
-    long long seg[5] = {0, 0, 0, 0, 0};      // trace: cycles before / in / after a chunk's steps, chunks entered without logits, chunks that prefetched
     // one chunk of (up to) 16 rows from R: xc / hc hold its logits if `have`; xn / hn receive the next chunk's
     auto chunk = [&](int R, float2 (&xc)[kCh], float (&hc)[kCh / 2], bool have, float2 (&xn)[kCh], float (&hn)[kCh / 2]) __attribute__((always_inline)) -> bool {
         const int rows = min(kCh, n - R);
         const uint32_t xa = ring + (uint32_t(R) & rmask) * kRowBytes;
         const uint64_t slot0 = bnd_out + uint64_t(R & (kBnd - 1)) * 8u;           // (R is a multiple of 16: a chunk never wraps)
         bool have_next = false;
-        long long tc2 = 0;
-        const long long tc0 = tr ? clock64() : 0;
-        if (tr) { seg[3] += have ? 0 : 1; }
+
         if (HAS_NEXT) {
             // this chunk overwrites the slots of rows R - kBnd ..: the consumer must be past them
             const int need = R + rows + 1 - kBnd;
@@ -314,17 +314,6 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
                 // producer wrote (slots 2i, 2i + 1)
                 uint32_t spins = 0;
                 const uint32_t base = uint32_t((R - 2) & (kBnd - 1)) * 8u;
-#if ISP_MASC_POLL
-                {
-                    // Wait on ONE slot, the last this chunk needs, and sleep between looks: a waiting strip that re-reads all its
-                    // slots in a tight loop takes the shared-memory pipe away from the strip it is waiting for (measured: the
-                    // producer's steps 44 -> 76 cycles per row).  The latency this adds is a constant skew per strip, not per chunk.
-                    float v; int g;
-                    const long long t0 = tr ? clock64() : 0;
-                    for (;;) { ld_slot(bnd_in + uint32_t((R + kCh - 2) & (kBnd - 1)) * 8u, v, g); if (g == R + kCh - 1) break; __nanosleep(100); spin_check(spins); }
-                    if (tr) w_bnd += clock64() - t0;
-                }
-#endif
                 for (;;) {
                     bool ok = true;
                     float v0, v1; int g0, g1;
@@ -346,8 +335,6 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
 #pragma unroll
                 for (int k = 0; k < kCh; ++k) bv[k] = (R + k == 0) ? 0.0f : -CUDART_INF_F;     // Q[-1][-1] = 0 stands in for mas.py:11-12
             }
-            const long long tc1 = tr ? clock64() : 0;
-            if (tr) { seg[0] += tc1 - tc0; seg[4] += have_next ? 1 : 0; }
 #pragma unroll
             for (int k = 0; k < kCh / 2; ++k)
                 step2(R, k, xc[2 * k], xc[2 * k + 1], hc[k], bv[2 * k], bv[2 * k + 1], uint32_t(R & (kBnd - 1)) * 8u + uint32_t(2 * k) * 8u,
@@ -357,10 +344,7 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
 #pragma unroll
                 for (int k = 0; k < kCh / 2; ++k) put4(uint32_t(R & (kBnd - 1)) * 8u + uint32_t(2 * k) * 8u, bq[k]);
             }
-#else
-            if (HAS_NEXT) put4(uint32_t(R & (kBnd - 1)) * 8u + uint32_t(kCh - 2) * 8u, bq[kCh / 2 - 1]);
 #endif
-            if (tr) { tc2 = clock64(); seg[1] += tc2 - tc1; }
             sts_u64_if(bits_sa + uint32_t(R + (lane & (kCh - 1))) * 16u, ke, ko, lane < kCh);     // raw: even columns, odd columns (the mapper interleaves)
         } else {
             wait_landed(R + rows);
@@ -381,7 +365,6 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
         st_volatile_if_sa(ctl + 4u * (kCtlProg + uint32_t(s)), R + rows, lane0);
         if (HAS_PREV && lane0) st_relaxed_cluster(cons_out, R + rows);
         __syncwarp();
-        if (tr && tc2) seg[2] += clock64() - tc2;
         return have_next;
     };
 
@@ -394,7 +377,6 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
         have = chunk(R + kCh, xB, hB, have, xA, hA);
     }
     if (tr && lane0) { tr[2 + s] = gtimer(); tr[10 + 2 * s] = w_land; tr[11 + 2 * s] = w_bnd; }
-    if (tr && lane0) for (int i = 0; i < 5; ++i) tr[16 + 8 * s + i] = seg[i];
 }
 
 // =================================== the kernel ======================================================================
@@ -421,6 +403,7 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 
     // ---- set-up: control words, boundary tags, barriers ----
     for (uint32_t i = tid; i < (kCtlBytes + 2u * kBnd * 8u) / 4u; i += kThreads) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+    for (uint32_t i = tid; i < uint32_t(nblk) * kPlanes * 2u; i += kThreads) reinterpret_cast<uint32_t*>(smem_raw + p.off_carry)[i] = 0u;
     __syncthreads();
     if (tid == 0) {
         for (int st = 0; st < stages; ++st) mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 4 * kCtlFull) + st, 1);
@@ -509,8 +492,9 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         const uint32_t maps_sa = smem_sa + p.off_maps, carry_sa = smem_sa + p.off_carry, bits_sa = smem_sa + p.off_bits;
         if (act0) {
             const bool feed_next = int(rank) + 1 < nc && col0 + kColsCta < m;
-            const uint32_t carry_next = feed_next ? mapa(carry_sa, rank + 1) : 0u;
-            const uint32_t mapin_next = feed_next ? mapa(ctl + 4u * kCtlMapIn, rank + 1) : 0u;
+            // the carry words travel as {value, block tag} in one 64-bit relaxed store each: like the strips' boundary slots they are
+            // their own flags (a release / acquire pair per block costs the mapper a fence, ~1 us, and it fell behind the sweep)
+            const uint64_t carry_next = feed_next ? cluster_generic(mapa(carry_sa, rank + 1)) : 0ull;
             const uint32_t m23 = act1 ? 0xffffffffu : 0u;          // an inactive strip's words were never written
             // identity, low 6 bits of the column: bit c of word w is bit `pl` of 32 w + c
             const uint32_t idp = pl == 0 ? 0xaaaaaaaau : pl == 1 ? 0xccccccccu : pl == 2 ? 0xf0f0f0f0u : pl == 3 ? 0xff00ff00u : 0xffff0000u;
@@ -523,8 +507,13 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
                 while (ld_volatile_sa(ctl + 4u * kCtlProg) < rows_end || (act1 && ld_volatile_sa(ctl + 4u * (kCtlProg + 1)) < rows_end)) { __nanosleep(200); spin_check(spins); }
                 uint32_t cin = 0;
                 if (rank > 0) {
-                    while (ld_acquire_cluster_sa(ctl + 4u * kCtlMapIn) < blk + 1) { __nanosleep(200); spin_check(spins); }
-                    cin = lds_u32_(carry_sa + uint32_t(blk * kPlanes + pl) * 4u);
+                    for (;;) {
+                        float cv; int tag;
+                        ld_slot(carry_sa + uint32_t(blk * kPlanes + pl) * 8u, cv, tag);
+                        cin = __float_as_uint(cv);
+                        if (__all_sync(0xffffffffu, tag == blk + 1)) break;
+                        __nanosleep(100); spin_check(spins);
+                    }
                 }
                 {
                     // the strips leave a row as {even columns, odd columns} per strip: interleave into column order, one row per lane
@@ -556,14 +545,7 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
                     }
                 }
                 if (lane < kPlanes) sts_v4(maps_sa + uint32_t(blk * kPlanes + lane) * 16u, make_uint4(W0, W1, W2, W3));
-                if (feed_next) {
-#pragma unroll
-                    for (int q = 0; q < kPlanes; ++q) {
-                        const uint32_t v = __shfl_sync(0xffffffffu, cout, q);
-                        if (lane == 0) st_cluster_u32(carry_next + uint32_t(blk * kPlanes + q) * 4u, v);
-                    }
-                    if (lane == 0) st_release_cluster(mapin_next, blk + 1);
-                }
+                if (feed_next) st_slot_if(carry_next + uint64_t(blk * kPlanes + pl) * 8u, __uint_as_float(cout), blk + 1, lane < kPlanes);
                 __syncwarp();
             }
         }
@@ -580,9 +562,12 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             if (f == 1) { blk = ld_volatile_sa(ctl + 4u * kCtlHopBlk); j = ld_volatile_sa(ctl + 4u * kCtlHopJ); go = true; }
         }
         if (go) {
-            const uint64_t ent0 = cluster_generic(mapa(smem_sa + p.off_ent, 0));
+            // the entries (the path's column at each block's last row) go to THIS CTA's array inside the loop -- a store into another
+            // CTA followed by a shared load costs the chain ~200 cycles per hop -- and to CTA 0's, lanes in parallel, after it
+            const uint32_t ent_sa = smem_sa + p.off_ent;
+            const int blk_first = blk;
             while (blk >= 0 && j >= col0) {
-                st_generic_u16_if(ent0 + uint64_t(blk) * 2u, j, lane == 0);              // the path's column at the block's last row
+                if (lane == 0) sts_u16_(ent_sa + uint32_t(blk) * 2u, j);
                 const int cl = j - col0;
                 const uint32_t wv = lds_u32_(maps_sa + uint32_t(blk * kPlanes + pl) * 16u + uint32_t(cl >> 5) * 4u);
                 const uint32_t low6 = __ballot_sync(0xffffffffu, ((wv >> (cl & 31)) & 1u) != 0u) & 63u;
@@ -595,6 +580,11 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
                 st_cluster_u32(mapa(ctl + 4u * kCtlHopBlk, rank - 1), uint32_t(blk));
                 st_cluster_u32(mapa(ctl + 4u * kCtlHopJ, rank - 1), uint32_t(j));
                 st_release_cluster(mapa(ctl + 4u * kCtlHopFlag, rank - 1), 1);
+            }
+            __syncwarp();
+            if (rank != 0) {
+                const uint32_t ent0 = mapa(ent_sa, 0);
+                for (int bb = blk_first - lane; bb > blk; bb -= 32) st_cluster_u16(ent0 + uint32_t(bb) * 2u, lds_u16_(ent_sa + uint32_t(bb) * 2u));
             }
             __syncwarp();
         }
@@ -676,7 +666,7 @@ static bool make_layout(int T1max, Layout* L) {
     uint32_t off = kCtlBytes;
     L->off_bnd = off;   off += 2u * kBnd * 8u;
     L->off_ent = off;   off += (nblk * 2u + 15u) & ~15u;
-    L->off_carry = off; off += (nblk * kPlanes * 4u + 15u) & ~15u;
+    L->off_carry = off; off += (nblk * kPlanes * 8u + 15u) & ~15u;
     L->off_maps = off;  off += nblk * kPlanes * 16u;
     L->off_bits = off;  off += uint32_t(T1max) * 16u;
     off = (off + 127u) & ~127u;

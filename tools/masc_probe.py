@@ -53,7 +53,7 @@ def run(name):
         for c in range(nc):
             r = tr[b, c]
             us = lambda i: (r[i] - t0) / 1e3 if r[i] else float('nan')
-            print(f"  cta {c}: start {us(0):6.1f} setup {us(1):6.1f} | strips end {us(2):6.1f} {us(3):6.1f} loader {us(9):6.1f} fill {us(14):6.1f} | maps {us(4):6.1f} hops {us(5):6.1f} | sync {us(6):6.1f} walk {us(7):6.1f} end {us(8):6.1f} | waits (kcyc) land {r[10]/1e3:.1f} {r[12]/1e3:.1f} bnd {r[11]/1e3:.1f} {r[13]/1e3:.1f} | strip 0: top {r[16]/1e3:.1f} steps {r[17]/1e3:.1f} tail {r[18]/1e3:.1f} kcyc, {r[19]} chunks without logits, {r[20]} prefetched | strip 1: {r[24]/1e3:.1f} {r[25]/1e3:.1f} {r[26]/1e3:.1f} {r[27]} {r[28]}")
+            print(f"  cta {c}: start {us(0):6.1f} setup {us(1):6.1f} | strips end {us(2):6.1f} {us(3):6.1f} loader {us(9):6.1f} fill {us(14):6.1f} | maps {us(4):6.1f} hops {us(5):6.1f} | sync {us(6):6.1f} walk {us(7):6.1f} end {us(8):6.1f} | waits (kcyc) logits {r[10]/1e3:.1f} {r[12]/1e3:.1f} neighbour {r[11]/1e3:.1f} {r[13]/1e3:.1f}")
 
 
 for name in sys.argv[1:] or ["cfg4"]:
