@@ -135,15 +135,19 @@ def test_full_size_cfg3_against_oracle(cuda_device):
 
 
 def test_full_size_cfg4_long_form(cuda_device):
-    """BASELINE.json configs[3]: 512 tokens x 4096 frames, batch 16 (bits spill to the workspace)."""
+    """BASELINE.json configs[3]: 512 tokens x 4096 frames, batch 16: the cluster kernel by default (isp_mas_cluster.cu, 4 CTAs per
+    utterance), the single-CTA strip kernel with its bits spilled to the workspace when forced (v1, with and without TMA)."""
     w = synth.WORKLOADS["cfg4"]
     tl, ml = synth.workload_lengths(w)
     x = synth.noise_logits(w.batch, w.t1max, w.t2max, w.seed)
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
-    for mode in ("auto", "no_tma"):
-        set_mode(mode)
+    for mode in ({}, {"mas.impl": 1}, {"mas.impl": 1, "mas.no_tma": 1}):
+        for key, val in mode.items():
+            _lib.set_option(key, val)
         hard, dur, _ = run_cuda(x, tl, ml, cuda_device)
         assert_same(hard, dur, rh, rd, f"cfg4 mode={mode}")
+        for key in mode:
+            _lib.set_option(key, 0)
 
 
 def test_maximum_width(cuda_device):
