@@ -43,8 +43,14 @@
 #include "isp_internal.h"
 #include "isp_mas_ptx.cuh"
 
+#ifndef ISP_MASC_PF
+#define ISP_MASC_PF 2           // A/B: the next chunk's logit loads 0 in front of each round's shuffles, 1 after the round's arithmetic, 2 none (burst at the chunk's top)
+#endif
+#ifndef ISP_MASC_BITS_ROW
+#define ISP_MASC_BITS_ROW 1     // A/B: 1 = lane 0 stores each row's backpointer words, 0 = lane k keeps row k in registers until the chunk's end
+#endif
 #ifndef ISP_MASC_PUT_END
-#define ISP_MASC_PUT_END 0      // A/B: 1 = the chunk's boundary stores in one burst after its rounds, 0 = one per round
+#define ISP_MASC_PUT_END 1      // A/B: 1 = the chunk's boundary stores in one burst after its rounds, 0 = one per round
 #endif
 
 namespace isp {
@@ -241,7 +247,9 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
     uint4 bq[kCh / 2];
     auto step2 = [&](int R, int k, float2 xa, float2 xb, float ha, float bA, float bB, uint32_t slot, uint32_t pf, float2& na, float2& nb,
                      float& nh) __attribute__((always_inline)) {
+#if ISP_MASC_PF == 0
         if (pf) { na = lds_f32x2_(pf); nb = lds_f32x2_(pf + kRowBytes); nh = lds_f32(pf - 4u); }
+#endif
         const float t1 = __shfl_sync(0xffffffffu, q1, src);
         const float t0 = __shfl_sync(0xffffffffu, q0, src);
 
@@ -256,9 +264,17 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
         q1 = __fadd_rn(xb.y, fmaxf(n0, n1));
         const uint32_t ea = __ballot_sync(0xffffffffu, a0) & emask, oa = __ballot_sync(0xffffffffu, a1);
         const uint32_t eb = __ballot_sync(0xffffffffu, b0) & emask, ob = __ballot_sync(0xffffffffu, b1);
+#if ISP_MASC_BITS_ROW
+        sts_u64_if(bits_sa + uint32_t(R + 2 * k) * 16u, ea, oa, lane0);
+        sts_u64_if(bits_sa + uint32_t(R + 2 * k + 1) * 16u, eb, ob, lane0);
+#else
         const bool mine_a = lane == 2 * k, mine_b = lane == 2 * k + 1;
         ke = mine_a ? ea : ke; ko = mine_a ? oa : ko;
         ke = mine_b ? eb : ke; ko = mine_b ? ob : ko;
+#endif
+#if ISP_MASC_PF == 1
+        if (pf) { na = lds_f32x2_(pf); nb = lds_f32x2_(pf + kRowBytes); nh = lds_f32(pf - 4u); }      // after the round's arithmetic
+#endif
 #if ISP_MASC_PUT_END
         if (HAS_NEXT) bq[k] = make_uint4(__float_as_uint(n1), uint32_t(R + 2 * k + 1), __float_as_uint(q1), uint32_t(R + 2 * k + 2));
 #else
@@ -306,7 +322,11 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
                 for (int k = 0; k < kCh / 2; ++k) hc[k] = lds_f32(xa + uint32_t(2 * k) * kRowBytes - 4u);
             }
             // the next chunk's logits, if they are there already, are loaded round by round under this chunk's steps
+#if ISP_MASC_PF == 2
+            have_next = false;                                   // no prefetch: every chunk loads its logits in one burst at its top
+#else
             have_next = n - (R + kCh) >= kCh && ld_volatile_sa(landed_sa) >= R + 2 * kCh;
+#endif
             const uint32_t xb = ring + (uint32_t(R + kCh) & rmask) * kRowBytes;
             float bv[kCh];
             if (HAS_PREV) {
@@ -339,13 +359,16 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
             for (int k = 0; k < kCh / 2; ++k)
                 step2(R, k, xc[2 * k], xc[2 * k + 1], hc[k], bv[2 * k], bv[2 * k + 1], uint32_t(R & (kBnd - 1)) * 8u + uint32_t(2 * k) * 8u,
                       have_next ? xb + uint32_t(2 * k) * kRowBytes : 0u, xn[2 * k], xn[2 * k + 1], hn[k]);
+
 #if ISP_MASC_PUT_END
             if (HAS_NEXT) {
 #pragma unroll
                 for (int k = 0; k < kCh / 2; ++k) put4(uint32_t(R & (kBnd - 1)) * 8u + uint32_t(2 * k) * 8u, bq[k]);
             }
 #endif
+#if !ISP_MASC_BITS_ROW
             sts_u64_if(bits_sa + uint32_t(R + (lane & (kCh - 1))) * 16u, ke, ko, lane < kCh);     // raw: even columns, odd columns (the mapper interleaves)
+#endif
         } else {
             wait_landed(R + rows);
             for (int k = 0; k < rows; ++k) {
