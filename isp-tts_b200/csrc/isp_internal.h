@@ -40,6 +40,7 @@ int    mas_wide_forward(const float* logp, int64_t sB, int64_t sT1, const int64_
 bool   mas_cluster_supported(int B, int T1max, int T2max);
 size_t mas_cluster_workspace_bytes(int B, int T1max, int T2max);
 int    mas_cluster_set_option(const char* key, int value, int* prev);
+bool   mas_cluster_one_wave(int B, int T1max, int T2max);      // all B clusters co-resident (cudaOccupancyMaxActiveClusters)
 int    mas_cluster_forward(const float* logp, int64_t sB, int64_t sT1, const int64_t* text_len, const int64_t* mel_len, int B, int T1max,
                            int T2max, int16_t* attn_hard, int64_t* durations, int16_t* path, void* ws, cudaStream_t stream);
 

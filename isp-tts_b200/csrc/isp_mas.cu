@@ -903,11 +903,10 @@ int mas_forward(const float* logp, int64_t sB, int64_t sT1, int64_t sT2,
     const bool want2 = g_opt_impl == 0 || g_opt_impl == 2;
     const bool fits2 = want2 && !g_opt_bits_global && g_opt_slots != 3 && T2max <= ISP_MAS_MAX_T2 && mas2_supported(B, T1max, T2max);
     // One thread-block cluster per utterance (isp_mas_cluster.cu): everything from 641 to 1024 tokens (~10x the general kernel), and
-    // the long-form shapes below that where it measured faster than this file's single-CTA kernel (tools/masc_compare.py): several
-    // thousand frames x more than 384 tokens with all clusters co-resident -- BASELINE configs[3], 16 x 4096 x 512: 268 us against
-    // 280 us; at 2000 x 384 or with more clusters than fit one wave the single-CTA kernel wins and keeps the shape.
-    const bool cluster_long = T2max > 384 && T1max >= 3000 && (long long)B * ((T2max + 127) / 128) <= 148;
-    if (g_opt_impl == 0 && !fits2 && (T2max > ISP_MAS_MAX_T2 || cluster_long) && mas_cluster_supported(B, T1max, T2max))
+    // below that every shape outside isp_mas2.cu's range whose clusters all run at once (tools/masc_compare.py: BASELINE configs[3],
+    // 16 x 4096 x 512, 225 us against 280 us for this file's single-CTA kernel; 16 x 1000 x 300 90 against 94).  With a second wave
+    // of clusters the single-CTA kernel wins (37 x 2500 x 512: 276 against 189 us) and keeps the shape.
+    if (g_opt_impl == 0 && !fits2 && mas_cluster_supported(B, T1max, T2max) && (T2max > ISP_MAS_MAX_T2 || mas_cluster_one_wave(B, T1max, T2max)))
         return mas_cluster_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws, stream);
     if (T2max > ISP_MAS_MAX_T2 || g_opt_impl == 3)       // wider than the strip kernels: the general kernel (or forced, for tests)
         return mas_wide_forward(logp, sB, sT1, text_len, mel_len, B, T1max, T2max, attn_hard, durations, path, ws, stream);

@@ -464,28 +464,32 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             if (p.bulk) {
                 uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 4 * kCtlFull);
                 const uint64_t policy = policy_evict_first();
-                int ci = 0;                                        // next chunk to issue
-                for (int cc = 0; cc < nch; ++cc) {                 // next chunk to complete
-                    uint32_t spins = 0;
-                    for (;;) {
-                        while (ci < nch && ci < cc + stages && consumed() >= (ci + 1) * kCh - p.ring_rows) {
-                            const int R = ci * kCh, rows = min(kCh, n - R);
-                            uint64_t* bar = full + (ci % stages);
-                            // one box of 16 rows x 128 columns (columns past T2max and rows past T1max arrive as zeros): per-row bulk
-                            // copies cost the TMA unit ~50 ns each, more than a strip takes to consume the row
-                            if (lane == 0) {
-                                mbar_arrive_expect_tx(bar, uint32_t(kCh) * kRowBytes);
-                                tma_load_box(ring + (uint32_t(R) & rmask) * kRowBytes, &tmap, col0, R, b, smem_u32(bar), policy);
-                            }
-                            (void)rows;
-                            ++ci;
+                // issue and completion are decoupled: a loader that blocks on the oldest chunk's barrier cannot refill the slots the
+                // strips free meanwhile, and the ring drains to one chunk per TMA round trip
+                int ci = 0, cc = 0;                                // next chunk to issue / to complete
+                uint32_t spins = 0;
+                while (cc < nch) {
+                    bool did = false;
+                    while (ci < nch && ci < cc + stages && consumed() >= (ci + 1) * kCh - p.ring_rows) {
+                        const int R = ci * kCh;
+                        uint64_t* bar = full + (ci % stages);
+                        // one box of 16 rows x 128 columns (columns past T2max and rows past T1max arrive as zeros): per-row bulk
+                        // copies cost the TMA unit ~50 ns each, more than a strip takes to consume the row
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(bar, uint32_t(kCh) * kRowBytes);
+                            tma_load_box(ring + (uint32_t(R) & rmask) * kRowBytes, &tmap, col0, R, b, smem_u32(bar), policy);
                         }
-                        if (ci > cc) break;
-                        __nanosleep(40); spin_check(spins);
+                        ++ci;
+                        did = true;
                     }
-                    mbar_wait_idle_sa(smem_u32(full + (cc % stages)), uint32_t(cc / stages) & 1u);
-                    if (lane == 0) st_volatile_sa(ctl + 4u * kCtlLanded, min(n, (cc + 1) * kCh));
                     __syncwarp();
+                    while (cc < ci && mbar_test_sa(smem_u32(full + (cc % stages)), uint32_t(cc / stages) & 1u)) {
+                        ++cc;
+                        did = true;
+                        if (lane == 0) st_volatile_sa(ctl + 4u * kCtlLanded, min(n, cc * kCh));
+                    }
+                    __syncwarp();
+                    if (!did) { __nanosleep(40); spin_check(spins); }
                 }
             } else {
                 // rows that are not 16 B aligned (strided or odd T2max): through registers, one chunk at a time
@@ -717,6 +721,36 @@ int mas_cluster_set_option(const char* key, int value, int* prev) {
 
 // status word, the path's scratch, the debug trace (16 words per CTA)
 size_t mas_cluster_workspace_bytes(int B, int T1max, int) { return 256 + ((size_t(B) * T1max * 2 + 15) & ~size_t(15)) + size_t(B) * masc::kMaxCluster * 32 * 8; }
+
+// Do all B clusters of this shape run at once?  (A second wave doubles the kernel: the dispatcher then prefers the single-CTA
+// kernel.)  cudaOccupancyMaxActiveClusters knows the GPC packing; the answer is cached per (cluster size, shared memory).
+bool mas_cluster_one_wave(int B, int T1max, int T2max) {
+    masc::Layout L;
+    if (!mas_cluster_supported(B, T1max, T2max) || !masc::make_layout(T1max, &L)) return false;
+    const int nc = (T2max + masc::kColsCta - 1) / masc::kColsCta;
+    static thread_local struct { int nc; uint32_t smem; int dev; int clusters; } memo[8] = {};
+    static thread_local int used = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    for (int i = 0; i < used; ++i)
+        if (memo[i].nc == nc && memo[i].smem == L.total && memo[i].dev == dev) return B <= memo[i].clusters;
+    if (cudaFuncSetAttribute(masc::mas_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.total)) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(nc) * 148u, 1, 1);
+    cfg.blockDim = dim3(masc::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = L.total;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(nc);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, masc::mas_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (used < 8) { memo[used].nc = nc; memo[used].smem = L.total; memo[used].dev = dev; memo[used].clusters = clusters; ++used; }
+    return B <= clusters;
+}
 
 typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
