@@ -10,20 +10,22 @@
 // 8 strips.  Here the token axis is cut into CTAs of 128 columns, 2..8 CTAs form a cluster, and everything that crosses a CTA
 // boundary goes through distributed shared memory:
 //
-//   * Forward.  A strip warp owns 64 columns, lane l the columns l and l + 32 (so a ballot is 32 consecutive columns); a row
-//     step is two rotating shuffles, two selects, 2 x (compare, max, add, ballot).  Strip g + 1 runs at least one 16-row chunk
-//     behind strip g (a wavefront over strips); the one value that crosses a strip boundary per row -- Q[i][last column] --
-//     is written by the producer's lane 31 straight into the CONSUMER's shared memory (st.shared::cluster, the same code for a
-//     neighbour warp and a neighbour CTA) as a 64-bit word {row tag, value}: the tag makes the slot its own flag, so the chain
-//     warps never execute a fence.  Logits arrive by 1-D bulk copies (TMA), 16 rows per mbarrier, a ring of up to 128 rows; a
-//     loader warp turns the barriers into a plain counter (an mbarrier test costs a chain warp ~100 cycles).
-//   * Backpointers: 1 bit per cell, row-major words in the owning CTA's shared memory (16 B per row and CTA) -- never in HBM.
+//   * Forward.  A strip warp owns 64 columns, lane l the columns 2l and 2l + 1; one exchange with the left neighbour (two
+//     rotating shuffles) advances TWO rows, the neighbour's cell in between being recomputed in the lane.  Strip g + 1 runs one
+//     chunk of 32 rows behind strip g (a wavefront over strips); the one value that crosses a strip boundary per row --
+//     Q[i][last column] -- is written by the producer's lane 31 straight into the CONSUMER's shared memory (st.relaxed.cluster
+//     through a generic pointer, the same code for a neighbour warp and a neighbour CTA) as a 64-bit word {value, row tag}: the
+//     tag makes the slot its own flag, so the chain warps never execute a fence.  Logits arrive as tiled TMA boxes of 32 rows x
+//     128 columns, a ring of 128 rows; a loader warp turns the mbarriers into a plain counter (an mbarrier test costs a chain
+//     warp ~100 cycles).
+//   * Backpointers: 1 bit per cell in the owning CTA's shared memory (16 B per row and CTA) -- never in HBM.  The strips leave
+//     them as {even columns, odd columns} words; the mapper interleaves them into column order, one row per lane.
 //   * Backtrack, parallel over blocks of 32 rows.  j <- j - bit[i][j] is T1 dependent lookups; instead a mapper warp per CTA
 //     composes, per block, the map "column at the block's last row -> column above its first row" while the sweep is still
 //     running, bit-sliced: plane k of the map holds bit k of the target column for all 128 source columns, and a row is
 //     plane' = select(bits, plane << 1, plane) -- one funnel shift and one LOP3 per 32 columns.  Only the low 6 bits of the
 //     target are kept (a block moves a column by at most 32, so the source column disambiguates).  The shift crosses CTA
-//     boundaries: the mapper of CTA c hands the 32 values of its last column to CTA c + 1 per block (DSMEM, release/acquire).
+//     boundaries: the mapper of CTA c hands the 32 values of its last column to CTA c + 1 per block (DSMEM, tagged slots again).
 //     After the sweep T1/32 serial hops remain, handed from CTA to CTA as the path moves left; then every block walks its
 //     own 32 rows (one thread per block, bits read through ld.shared::cluster from whichever CTA owns the column).
 //   * Outputs: each CTA zero-fills a slice of the utterance's dense int16 rows under the sweep, writes that slice's ones after
@@ -58,13 +60,16 @@ namespace masc {
 
 constexpr int kStrip = 64;              // columns per strip warp
 constexpr int kColsCta = 128;           // two strips per CTA
-constexpr int kCh = 16;                 // rows per chunk = rows per mbarrier
+#ifndef ISP_MASC_KCH
+#define ISP_MASC_KCH 32
+#endif
+constexpr int kCh = ISP_MASC_KCH;                 // rows per chunk = rows per mbarrier
 constexpr int kBnd = 256;               // slots of a strip's boundary-in ring (8 B each)
 constexpr int kPlanes = 6;              // low bits of a column index kept in a block map
 constexpr int kBlk = 32;                // rows per backtrack block
 constexpr int kThreads = 256;           // warps: 0, 1 strips; 2 loader; 3 mapper + hops; 4..7 zero fill
 constexpr int kMaxCluster = 8;
-constexpr int kMaxStages = 8;           // ring of at most 128 rows
+constexpr int kMaxStages = 128 / kCh;           // ring of at most 128 rows
 constexpr uint32_t kRowBytes = kColsCta * 4;
 
 // control block (32-bit words from off_ctl)
@@ -210,11 +215,11 @@ ISP_DEVINL void spin_check(uint32_t& spins) { if (++spins > (1u << 25)) __trap()
 // Lane l owns the strip's columns 2l and 2l + 1.  A round advances TWO rows on one exchange: the lane takes its left
 // neighbour's two values of row r - 1 (two rotating shuffles), recomputes the neighbour's cell Q[r][2l-1] itself (the halo:
 // same operands, same fp32 operations, so the same bits), and then has everything rows r and r + 1 need.
-// What bounds a strip is not arithmetic but the warp's traffic through the SM's memory-instruction queue (shuffles, shared
-// loads and stores, the stores into the neighbour: ~8 cycles apiece for one warp, tools/ubench/shfl2.cu), so per two rows
-// there are two shuffles, three loads (the NEXT chunk's logits, spread over the rounds so that they never queue in front of
-// a shuffle), one 16 B store of two boundary slots -- and the backpointer words stay in registers (lane k keeps row k of the
-// chunk) until one store per 16 rows.
+// What bounds a strip is one warp's dependent chain and whatever shares the SM's memory-instruction queue with the two
+// shuffles of a round, and the generated code is very sensitive to its schedule.  The one that ships was chosen by measurement
+// among seven builds (cfg4 268 -> 217 us): a chunk's logits in ONE burst of loads at its top (no
+// prefetch inside the rounds), the backpointer words stored per row by lane 0, the chunk's boundary values assembled as
+// {value, tag} pairs in register quads of their own and stored in one burst after its rounds, 32 rows per chunk.
 // HAS_PREV: a strip on the left feeds this one's column 0; HAS_NEXT: this strip feeds one on the right.
 template <bool HAS_PREV, bool HAS_NEXT>
 ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, int lane, int n, uint32_t rank, long long* tr) {
@@ -236,14 +241,13 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
     const uint32_t landed_sa = ctl + 4u * kCtlLanded, cons_in = ctl + 4u * (kCtlCons + uint32_t(s));
     const uint32_t emask = HAS_PREV ? 0xffffffffu : 0xfffffffeu;                         // global column 0 never moves (mas.py:16)
     float q0 = -CUDART_INF_F, q1 = -CUDART_INF_F;
-    uint32_t ke = 0, ko = 0;        // lane k < 16: the backpointer words (even columns, odd columns) of row k of the current chunk
+    uint32_t ke = 0, ko = 0;        // (ISP_MASC_BITS_ROW == 0: lane k keeps the backpointer words of row k of the current chunk)
 
     // Q[r][j] = x[r][j] + max(Q[r-1][j-1], Q[r-1][j]), bit = Q[r-1][j-1] >= Q[r-1][j]   (mas.py:14, :17)
     // rows r = R + 2k and r + 1; bA = Q[r-1][-1], bB = Q[r][-1] of this strip (the strip on the left, or the virtual Q[-1][-1] = 0 / -inf)
-    // pf: address of the even row of the next chunk's logits for this round (0 = none), loaded in front of the round's shuffles;
-    // the round's two boundary values leave as one 16 B store of two {value, tag} slots at its end.  (Measured alternatives, all
-    // slower on cfg4: the loads behind the shuffles, the chunk's stores in one burst after its rounds, the pairs assembled in
-    // register quads of their own, weak / plain shared stores -- DESIGN.md section 4.2.)
+    // (ISP_MASC_PF / ISP_MASC_BITS_ROW / ISP_MASC_PUT_END select the schedules that were measured against each other; the
+    // defaults are what ships.  pf: address of the even row of the next chunk's logits for this round, 0 = none -- always 0 with
+    // ISP_MASC_PF == 2.)
     uint4 bq[kCh / 2];
     auto step2 = [&](int R, int k, float2 xa, float2 xb, float ha, float bA, float bB, uint32_t slot, uint32_t pf, float2& na, float2& nb,
                      float& nh) __attribute__((always_inline)) {
@@ -300,7 +304,7 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
             if (tr) w_land += clock64() - t0;
         }
     };
-    // one chunk of (up to) 16 rows from R: xc / hc hold its logits if `have`; xn / hn receive the next chunk's
+    // one chunk of (up to) kCh rows from R: xc / hc hold its logits if `have`; xn / hn receive the next chunk's (ISP_MASC_PF != 2)
     auto chunk = [&](int R, float2 (&xc)[kCh], float (&hc)[kCh / 2], bool have, float2 (&xn)[kCh], float (&hn)[kCh / 2]) __attribute__((always_inline)) -> bool {
         const int rows = min(kCh, n - R);
         const uint32_t xa = ring + (uint32_t(R) & rmask) * kRowBytes;
@@ -473,7 +477,7 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
                     while (ci < nch && ci < cc + stages && consumed() >= (ci + 1) * kCh - p.ring_rows) {
                         const int R = ci * kCh;
                         uint64_t* bar = full + (ci % stages);
-                        // one box of 16 rows x 128 columns (columns past T2max and rows past T1max arrive as zeros): per-row bulk
+                        // one box of kCh rows x 128 columns (columns past T2max and rows past T1max arrive as zeros): per-row bulk
                         // copies cost the TMA unit ~50 ns each, more than a strip takes to consume the row
                         if (lane == 0) {
                             mbar_arrive_expect_tx(bar, uint32_t(kCh) * kRowBytes);
@@ -756,7 +760,7 @@ typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// (T2max, T1max, B) fp32, box 128 columns x 16 rows: what one CTA of a cluster takes per chunk
+// (T2max, T1max, B) fp32, box 128 columns x kCh rows: what one CTA of a cluster takes per chunk
 static bool make_cluster_map(CUtensorMap* map, const float* logp, int64_t sB, int64_t sT1, int B, int T1max, int T2max) {
     static PFN_encodeTiledC enc = nullptr;
     if (!enc) {
