@@ -48,6 +48,9 @@
 #include "isp_internal.h"
 #include "isp_mas_ptx.cuh"
 
+#ifndef ISP_MAS2_PROBE
+#define ISP_MAS2_PROBE 0
+#endif
 #ifndef ISP_MAS2_SHFL
 #define ISP_MAS2_SHFL 0
 #endif
@@ -473,7 +476,11 @@ mas2_kernel(const __grid_constant__ Maps maps, const Params p) {
     const uint32_t tdone_sa = hdr_sa + kOffTdone, mdone_sa = hdr_sa + kOffMdone;
     const uint32_t filldone_sa = hdr_sa + kOffFillDone;
     const uint32_t slot0_done_sa = smem_sa + kZeroPage + kOffSlotDone;
+#if ISP_MAS2_PROBE
     const bool probe_w = p.probe != nullptr && rank0 == 0 && slot == 0 && s == 0;
+#else
+    const bool probe_w = false;       // (the phase probe of tools/mas2_probe.py is a build option: tools/ab_build.sh probe isp_mas2.cu -DISP_MAS2_PROBE=1)
+#endif
 
     // the zero page and slot 0's "done" flag belong to the CTA: set up by slot 0's filler before anybody needs them
     if (role == 2 && slot == 0) {

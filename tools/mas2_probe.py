@@ -1,6 +1,9 @@
 """Debug aid: phase timing of isp_mas2.cu (SM clocks of the longest utterance) and kernel time for a workload.
 
     python tools/mas2_probe.py cfg2 cfg3 cfg3d      # env: PROBE_IMPL=0,1  PROBE_SLOTS=0,1,2
+
+The phase counters are a BUILD option of the kernel (compiled in, they cost the shipped kernel 3 %):
+    bash tools/ab_build.sh probe isp_mas2.cu -DISP_MAS2_PROBE=1 && ISP_TTS_B200_LIB=tools/_ab/lib_probe.so python tools/mas2_probe.py cfg3
 """
 import os
 import sys
