@@ -216,10 +216,16 @@ ISP_DEVINL void store_chunk(const float* stage, float* gbase, int lane, int row0
     }
 }
 
-template <bool TF32>
+// DBG: the debug options (loglik.debug_scores, align.trace) live in an instantiation of their own, so that the production kernel
+// does not carry their branches (in the MAS kernels, instrumentation that is compiled in but never executed cost 3-20 %)
+template <bool TF32, bool DBG>
 __global__ void __launch_bounds__(kThreads, 2)
 loglik_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-              const LoglikParams p) {
+              const LoglikParams pp) {
+    struct P : LoglikParams {
+        __device__ P(const LoglikParams& o) : LoglikParams(o) { if (!DBG) { debug_scores = 0; tstamp = nullptr; } }
+    };
+    const P p(pp);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -817,15 +823,18 @@ int loglik_forward(const void* Q, const void* K, int dtype, const int64_t* text_
     if (smem > 227 * 1024) { set_error("isp_loglik_forward: needs %zu B of shared memory (T2max=%d, D=%d)", smem, T2max, D); return ISP_ERR_UNSUPPORTED; }
 
     const dim3 grid((T1max + kTileM - 1) / kTileM, B);
+    const bool dbg = p.debug_scores != 0 || p.tstamp != nullptr;
     cudaError_t e;
     if (dtype == ISP_DTYPE_F32) {
-        e = cudaFuncSetAttribute(loglik_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        auto kern = dbg ? loglik_kernel<true, true> : loglik_kernel<true, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(loglik_kernel<tf32>)");
-        loglik_kernel<true><<<grid, kThreads, smem, stream>>>(mq, mk, p);
+        kern<<<grid, kThreads, smem, stream>>>(mq, mk, p);
     } else {
-        e = cudaFuncSetAttribute(loglik_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        auto kern = dbg ? loglik_kernel<false, true> : loglik_kernel<false, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(loglik_kernel<bf16>)");
-        loglik_kernel<false><<<grid, kThreads, smem, stream>>>(mq, mk, p);
+        kern<<<grid, kThreads, smem, stream>>>(mq, mk, p);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "loglik_kernel launch");
