@@ -45,6 +45,18 @@
 #include "isp_internal.h"
 #include "isp_mas_ptx.cuh"
 
+#ifndef ISP_MASC_BNDSLEEP
+#define ISP_MASC_BNDSLEEP 20    // ns between two looks at the strip on the left's slots
+#endif
+#ifndef ISP_MASC_LDSLEEP
+#define ISP_MASC_LDSLEEP 40     // ns between two rounds of the loader when it had nothing to do
+#endif
+#ifndef ISP_MASC_MAPPOLL
+#define ISP_MASC_MAPPOLL 200    // ns between two looks of the mapper at its strips' progress
+#endif
+#ifndef ISP_MASC_FILLPACE
+#define ISP_MASC_FILLPACE 100   // ns between two 16 B zero-fill stores of a filler thread
+#endif
 #ifndef ISP_MASC_PF
 #define ISP_MASC_PF 2           // A/B: the next chunk's logit loads 0 in front of each round's shuffles, 1 after the round's arithmetic, 2 none (burst at the chunk's top)
 #endif
@@ -352,7 +364,7 @@ ISP_DEVINL void sweep(const Params& p, uint32_t smem_sa, uint32_t ctl, int s, in
                     }
                     if (ok) break;
                     const long long t0 = tr ? clock64() : 0;
-                    __nanosleep(20); spin_check(spins);
+                    __nanosleep(ISP_MASC_BNDSLEEP); spin_check(spins);
                     if (tr) w_bnd += clock64() - t0;
                 }
             } else {
@@ -493,7 +505,7 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
                         if (lane == 0) st_volatile_sa(ctl + 4u * kCtlLanded, min(n, cc * kCh));
                     }
                     __syncwarp();
-                    if (!did) { __nanosleep(40); spin_check(spins); }
+                    if (!did) { __nanosleep(ISP_MASC_LDSLEEP); spin_check(spins); }
                 }
             } else {
                 // rows that are not 16 B aligned (strided or odd T2max): through registers, one chunk at a time
@@ -535,7 +547,7 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             for (int blk = 0; blk < nblk; ++blk) {
                 const int rows_end = min(n, kBlk * (blk + 1));
                 uint32_t spins = 0;
-                while (ld_volatile_sa(ctl + 4u * kCtlProg) < rows_end || (act1 && ld_volatile_sa(ctl + 4u * (kCtlProg + 1)) < rows_end)) { __nanosleep(200); spin_check(spins); }
+                while (ld_volatile_sa(ctl + 4u * kCtlProg) < rows_end || (act1 && ld_volatile_sa(ctl + 4u * (kCtlProg + 1)) < rows_end)) { __nanosleep(ISP_MASC_MAPPOLL); spin_check(spins); }
                 uint32_t cin = 0;
                 if (rank > 0) {
                     for (;;) {
@@ -631,7 +643,7 @@ mas_cluster_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         const size_t n16 = (total - head) >> 3;
         uint4* v = reinterpret_cast<uint4*>(base + head);
         // paced: an unpaced fill of every cluster at once saturates HBM for its duration and starves the sweeps' loaders
-        const unsigned pace = n > 512 ? 100u : 0u;
+        const unsigned pace = n > 512 ? unsigned(ISP_MASC_FILLPACE) : 0u;
         for (size_t i = ft; i < n16; i += nft) { st_cs_v4(v + i, make_uint4(0u, 0u, 0u, 0u)); if (pace) __nanosleep(pace); }
         for (size_t i = head + (n16 << 3) + ft; i < total; i += nft) base[i] = 0;
         if (tr && ft == 0) tr[14] = gtimer();
