@@ -161,3 +161,16 @@ def test_no_binaries_tracked_and_runtime_linked_dynamically():
         blob = open(so, "rb").read()
         for nm in names:
             assert nm not in blob, f"{nm.decode()} is named inside libisp_tts_b200.so (static cudart?)"
+
+
+def test_precision_modes_of_the_drop_in():
+    """ConvAttention.gemm_dtype: "auto" = the reference's own precision (fp32-faithful products outside autocast, bf16 under CUDA autocast:
+    tests/test_gpu_aligner.py),
+    "tf32" = the fused single-pass kernel on fp32 operands (host logic only: no kernel is launched here)."""
+    from isp_tts_b200.alignment import ConvAttention
+    att = ConvAttention(mel_dim=8, text_dim=12, attention_dim=16)
+    assert att.gemm_dtype == "auto" and att._mode() == "fp32" and att._precision() == "fp32"
+    att.gemm_dtype = "tf32"
+    assert att._mode() == "tf32" and att._precision() == "tf32"
+    att.gemm_dtype = "bf16"
+    assert att._mode() == "bf16"
