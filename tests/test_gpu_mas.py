@@ -189,8 +189,11 @@ def test_wide_utterances_general_kernel(cuda_device, shape):
         assert np.array_equal(got[b, :ml[b]], ref_path[b, :ml[b]]) and np.all(got[b, ml[b]:] == -1)
 
 
-def test_unaligned_and_strided_inputs(cuda_device):
-    """Rows that are not 16 B aligned take the non-TMA producer path; padded row strides too."""
+@pytest.mark.parametrize("mode", ["auto", "cluster"])
+def test_unaligned_and_strided_inputs(cuda_device, mode):
+    """Rows that are not 16 B aligned take the non-TMA producer path; padded row strides too (also on the cluster kernel, whose
+    tensor map then carries the padded stride)."""
+    set_mode(mode)
     rs = np.random.RandomState(3)
     for (B, T1, T2) in [(3, 50, 33), (2, 64, 7), (4, 31, 1), (2, 1, 9)]:
         x = (np.rint(rs.standard_normal((B, T1, T2)) * 4) / 4).astype(np.float32)
@@ -208,6 +211,15 @@ def test_unaligned_and_strided_inputs(cuda_device):
     hard, dur = mas_forward(view, torch.from_numpy(tl), torch.from_numpy(ml))
     rh, rd = omas.b_mas_with_durations(x, tl, ml)
     assert_same(hard.cpu().numpy(), dur.cpu().numpy(), rh, rd, "strided view")
+    # 16 B aligned rows with a padded stride and a padded batch stride: the TMA path with strides that are not the extents
+    buf = torch.zeros(3 * 70 * 48 + 64, device=cuda_device)
+    x = (np.rint(rs.standard_normal((3, 66, 40)) * 2) / 2).astype(np.float32)
+    view = buf[: 3 * 70 * 48].view(3, 70, 48)[:, :66, :40]
+    view.copy_(torch.from_numpy(x))
+    tl, ml = np.array([40, 17, 33]), np.array([66, 66, 9])
+    hard, dur = mas_forward(view, torch.from_numpy(tl), torch.from_numpy(ml))
+    rh, rd = omas.b_mas_with_durations(x, tl, ml)
+    assert_same(hard.cpu().numpy(), dur.cpu().numpy(), rh, rd, "aligned strided view")
 
 
 def test_reference_entry_points(cuda_device):
