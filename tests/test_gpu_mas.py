@@ -240,7 +240,9 @@ def test_reference_entry_points(cuda_device):
     assert torch.equal(log_p, attn_logits)
 
 
-def test_out_of_contract_lengths_are_reported(cuda_device):
+@pytest.mark.parametrize("mode", ["auto", "v1", "wide", "cluster"])
+def test_out_of_contract_lengths_are_reported(cuda_device, mode):
+    set_mode(mode)
     x = torch.zeros(3, 8, 5, device=cuda_device)
     with pytest.raises(_lib.IspError):
         mas_forward(x, torch.tensor([5, 9, 2]), torch.tensor([8, 8, 0]), check_lengths=True)
